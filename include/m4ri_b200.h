@@ -1,0 +1,126 @@
+/* m4ri_b200.h — C-ABI of libm4ri_b200.so: a B200 (sm_100a) drop-in for the dense
+ * GF(2) multiplication path of M4RI (malb/m4ri @ 5d0d0ce).
+ *
+ * Part 1 re-declares the reference's own types and entry points, with the file:line
+ * of the reference declaration each one replaces.  A program that includes
+ * <m4ri/m4ri.h> and links libm4ri_b200.so before libm4ri.so (or LD_PRELOADs it)
+ * gets these symbols from here; everything else (mzd_init, mzd_free, PLE, TRSM, ...)
+ * keeps coming from libm4ri.  See INTEGRATION.md.
+ *
+ * Part 2 is the device-resident extension API (m4ri_b200_*): explicit device
+ * matrices, uploads/downloads and the kernels without the host round trip.  Plain
+ * pointers and sizes only; no C++/torch types.
+ *
+ * Error convention = the reference's: invalid arguments and CUDA failures print to
+ * stderr and abort() (m4ri_die, m4ri/misc.c:36-42).  There is no CPU fallback: if no
+ * CUDA device is usable the call dies.
+ */
+#ifndef M4RI_B200_H
+#define M4RI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Part 1: reference ABI ------------------------------------------------------- */
+
+#ifndef M4RI_MISC_H            /* m4ri/misc.h:64-87 */
+typedef int      BIT;
+typedef int      rci_t;        /* row/column index */
+typedef int64_t  wi_t;         /* word index */
+typedef uint64_t word;         /* 64 matrix entries, column j in bit j%64 (LSB first) */
+#define m4ri_radix 64
+#endif
+
+#ifndef M4RI_MZD_H             /* m4ri/mzd.h:68-99 — 64-byte header, layout asserted in capi.cpp */
+typedef struct mzd_t {
+  rci_t   nrows;
+  rci_t   ncols;
+  wi_t    width;               /* ceil(ncols/64) */
+  wi_t    rowstride;           /* words between consecutive rows */
+  uint8_t flags;               /* 0x2 non-zero excess, 0x4 windowed (mzd.h:144,150) */
+  uint8_t padding[63 - 2 * sizeof(rci_t) - 2 * sizeof(wi_t) - sizeof(word) - sizeof(void *)];
+  word    high_bitmask;        /* valid bits of word width-1 */
+  word   *data;                /* row i at data + i*rowstride (mzd.h:185-187) */
+} mzd_t;
+#endif
+
+/* C = A*B, Strassen-Winograd above the M4RM leaf.  C may be NULL (allocated, caller
+ * frees with mzd_free).  cutoff 0 = library default, <0 dies.  m4ri/strassen.h:68,
+ * strassen.c:345-365. */
+mzd_t *mzd_mul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
+/* C ^= A*B.  m4ri/strassen.h:88, strassen.c:675-700. */
+mzd_t *mzd_addmul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
+/* unchecked variants.  m4ri/strassen.h:52,109,126; strassen.c:41,367,667. */
+mzd_t *_mzd_mul_even(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
+mzd_t *_mzd_addmul_even(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
+mzd_t *_mzd_addmul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
+/* M4RM only (no Strassen).  k = table bits, 0 = auto; any k gives the same bits, the
+ * device kernel always uses its own k.  m4ri/brilliantrussian.h:274,291,317;
+ * brilliantrussian.c:999-1190. */
+mzd_t *mzd_mul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k);
+mzd_t *mzd_addmul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k);
+mzd_t *_mzd_mul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k, int clear);
+/* block-parallel multiply: the reference splits C 2x2 over four OpenMP sections
+ * (m4ri/mp.h:47,62; mp.c:277-324); here C's row-blocks are split over the visible
+ * GPUs (m4ri_b200_set_num_devices). */
+mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
+mzd_t *mzd_addmul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
+
+/* ---- Part 2: extension API --------------------------------------------------------- */
+
+/* Library / device control. */
+int         m4ri_b200_version(void);
+int         m4ri_b200_device_count(void);
+void        m4ri_b200_set_device(int device);          /* device used by this process (default: current) */
+void        m4ri_b200_set_num_devices(int n);           /* GPUs used by mzd_mul_mp (default 1) */
+void        m4ri_b200_set_default_cutoff(int cutoff);   /* Strassen leaf size used when cutoff==0 */
+int         m4ri_b200_get_default_cutoff(void);
+void        m4ri_b200_release(void);                    /* free cached device workspaces */
+char const *m4ri_b200_last_path(void);                  /* "m4rm" / "strassen:<levels>" of the last product */
+uint64_t    m4ri_b200_kernel_launches(void);            /* CUDA kernels launched by this library so far */
+
+/* Stand-alone host matrices (same layout/semantics as mzd_init / mzd_init_window /
+ * mzd_free, m4ri/mzd.c:142-185) for programs that do not link libm4ri. */
+mzd_t *m4ri_b200_mzd_init(rci_t r, rci_t c);
+mzd_t *m4ri_b200_mzd_init_window(mzd_t *M, rci_t lowr, rci_t lowc, rci_t highr, rci_t highc);
+void   m4ri_b200_mzd_free(mzd_t *M);
+
+/* Device-resident matrix: bit-packed rows exactly like mzd_t (64-bit words, LSB-first),
+ * pitch a multiple of 2 words, base 16-byte aligned, and every bit between ncols and
+ * the pitch zero. */
+typedef struct m4ri_b200_dmat {
+  word   *data;      /* device pointer */
+  int64_t pitch;     /* words between rows */
+  rci_t   nrows;
+  rci_t   ncols;
+  int     owner;     /* 1: data was allocated by m4ri_b200_dmat_alloc */
+} m4ri_b200_dmat;
+
+m4ri_b200_dmat *m4ri_b200_dmat_alloc(rci_t nrows, rci_t ncols);   /* zero-filled */
+/* wrap caller-owned device memory (e.g. a torch tensor): ptr 16-byte aligned, pitch_words
+ * even and >= ceil(ncols/128)*2, padding bits must be zero. */
+m4ri_b200_dmat *m4ri_b200_dmat_wrap(void *device_ptr, int64_t pitch_words, rci_t nrows, rci_t ncols);
+void            m4ri_b200_dmat_free(m4ri_b200_dmat *M);
+/* host mzd_t (any window/stride/excess) -> device (excess bits cleared) and back (bits of
+ * the host matrix outside nrows x ncols are preserved).  stream: cudaStream_t or NULL. */
+void m4ri_b200_upload(m4ri_b200_dmat *dst, mzd_t const *src, void *stream);
+void m4ri_b200_download(mzd_t *dst, m4ri_b200_dmat const *src, void *stream);
+void m4ri_b200_sync(void *stream);
+
+/* C (^)= A*B on device matrices, asynchronous on `stream`.
+ *   dmul_m4rm : the M4RM leaf kernel only (config "mzd_mul_m4rm").
+ *   dmul      : Strassen-Winograd down to `cutoff`, then the leaf (config "mzd_mul").
+ * clear != 0 computes C = A*B, clear == 0 computes C ^= A*B. */
+void m4ri_b200_dmul_m4rm(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int clear, void *stream);
+void m4ri_b200_dmul(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int cutoff, int clear, void *stream);
+/* C = A ^ B on device matrices (the device form of _mzd_add, m4ri/mzd.c:1471-1583). */
+void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M4RI_B200_H */

@@ -1,0 +1,395 @@
+// capi.cu — the C-ABI of libm4ri_b200.so (include/m4ri_b200.h).
+//
+// Host side of the drop-in: argument checks and error behaviour of the reference entry points
+// (m4ri/strassen.c:345-365, 675-700; m4ri/brilliantrussian.c:999-1028), then
+//   host mzd_t --H2D--> zero-padded device matrices --kernels--> --D2H--> host mzd_t
+// honouring rowstride, windows and excess bits exactly as the reference does (m4ri/mzd.h:117-122).
+// There is no CPU compute path in this file: without a CUDA device every entry point dies.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "dev.h"
+#include "workspace.h"
+
+namespace m4b {
+
+void die(char const *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vfprintf(stderr, fmt, ap);
+  va_end(ap);
+  abort();
+}
+
+static_assert(sizeof(mzd_t) == 64, "mzd_t must be 64 bytes (m4ri/mzd.c:143)");
+static_assert(offsetof(mzd_t, nrows) == 0 && offsetof(mzd_t, ncols) == 4 && offsetof(mzd_t, width) == 8 &&
+                  offsetof(mzd_t, rowstride) == 16 && offsetof(mzd_t, flags) == 24 &&
+                  offsetof(mzd_t, high_bitmask) == 48 && offsetof(mzd_t, data) == 56,
+              "mzd_t layout differs from m4ri/mzd.h:68-99");
+
+namespace {
+
+constexpr uint8_t kFlagExcess = 0x2, kFlagWindow = 0x4;
+constexpr int kBuiltinCutoff = 8192;   // device Strassen leaf size; tuned on B200, see DESIGN.md
+
+struct Ctx {
+  bool         ready = false;
+  int          device = -1;            // -1: whatever is current at first use
+  int          num_devices = 1;
+  int          default_cutoff = 0;
+  cudaStream_t stream = nullptr;
+  Workspace    ws;
+  std::vector<word> host_tmp;
+  char         last_path[64] = "none";
+};
+Ctx g;
+
+Ctx &ctx() {
+  if (!g.ready) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      die("m4ri_b200: no usable CUDA device (%s); this library has no CPU fallback\n", cudaGetErrorString(e));
+    if (g.device >= 0) M4B_CUDA(cudaSetDevice(g.device));
+    M4B_CUDA(cudaGetDevice(&g.device));
+    M4B_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    if (!g.default_cutoff) {
+      char const *env = getenv("M4RI_B200_CUTOFF");
+      g.default_cutoff = env && atoi(env) > 0 ? atoi(env) : kBuiltinCutoff;
+    }
+    g.ready = true;
+  }
+  return g;
+}
+
+inline int round_up(int v, int mult) { return (int)(((int64_t)v + mult - 1) / mult * mult); }
+
+word left_mask(int nbits) { return ~(word)0 >> ((64 - nbits) % 64); }
+
+// ---- stand-alone host matrices ------------------------------------------------------
+void fill_header(mzd_t *M, rci_t r, rci_t c) {
+  memset(M, 0, sizeof *M);
+  M->nrows = r;
+  M->ncols = c;
+  M->width = c > 0 ? (c + 63) / 64 : 0;
+  M->high_bitmask = left_mask(c % 64);
+  if (c % 64) M->flags |= kFlagExcess;
+}
+
+typedef mzd_t *(*mzd_init_fn)(rci_t, rci_t);
+
+// A NULL result matrix must be freeable by the caller's mzd_free (m4ri/strassen.c:356-357): when a
+// libm4ri is loaded in the process use ITS mzd_init, otherwise our own (m4ri_b200_mzd_free).
+mzd_t *alloc_result(rci_t r, rci_t c) {
+  static mzd_init_fn ref_init = reinterpret_cast<mzd_init_fn>(dlsym(RTLD_DEFAULT, "mzd_init"));
+  return ref_init ? ref_init(r, c) : m4ri_b200_mzd_init(r, c);
+}
+
+// ---- transfers --------------------------------------------------------------------------
+void upload(DView dst, mzd_t const *src, cudaStream_t s) {
+  if (src->nrows == 0 || src->ncols == 0) return;
+  M4B_CUDA(cudaMemcpy2DAsync(dst.data, (size_t)dst.pitch * 8, src->data, (size_t)src->rowstride * 8,
+                             (size_t)src->width * 8, (size_t)src->nrows, cudaMemcpyHostToDevice, s));
+  if (src->ncols % 64) launch_mask_excess(DView{dst.data, dst.pitch, src->nrows, src->ncols}, s);
+}
+
+// Device rows -> host matrix, touching only bits (i < nrows, j < ncols) of the host matrix.
+void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp) {
+  if (dst->nrows == 0 || dst->ncols == 0) return;
+  int64_t const full = dst->ncols / 64;   // whole words per row
+  if (full)
+    M4B_CUDA(cudaMemcpy2DAsync(dst->data, (size_t)dst->rowstride * 8, src.data, (size_t)src.pitch * 8,
+                               (size_t)full * 8, (size_t)dst->nrows, cudaMemcpyDeviceToHost, s));
+  if (dst->ncols % 64) {
+    tmp.resize((size_t)dst->nrows);
+    M4B_CUDA(cudaMemcpy2DAsync(tmp.data(), 8, src.data + full, (size_t)src.pitch * 8, 8, (size_t)dst->nrows,
+                               cudaMemcpyDeviceToHost, s));
+    M4B_CUDA(cudaStreamSynchronize(s));
+    word const mask = dst->high_bitmask;
+    for (rci_t i = 0; i < dst->nrows; ++i) {
+      word *w = dst->data + (int64_t)i * dst->rowstride + full;
+      *w = (*w & ~mask) | (tmp[(size_t)i] & mask);
+    }
+  }
+}
+
+void zero_async(DView v, cudaStream_t s) {
+  M4B_CUDA(cudaMemsetAsync(v.data, 0, (size_t)v.nrows * (size_t)v.pitch * 8, s));
+}
+
+int norm_cutoff(int cutoff, char const *who) {   // m4ri/strassen.c:349-354
+  if (cutoff < 0) die("%s: cutoff must be >= 0.\n", who);
+  if (cutoff == 0) cutoff = ctx().default_cutoff;
+  cutoff = cutoff / 64 * 64;
+  return cutoff < 64 ? 64 : cutoff;
+}
+
+// The one host->device->host product path behind every reference-named entry point.
+void host_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool clear, bool strassen) {
+  Ctx &c = ctx();
+  int const m = A->nrows, l = A->ncols, n = B->ncols;
+  if (m == 0 || n == 0) return;
+  int const levels = (strassen && l > 0) ? strassen_levels(m, l, n, cutoff) : 0;
+  int const mp = round_up(m, 1 << levels), lp = round_up(l > 0 ? l : 1, 128 << levels), np = round_up(n, 128 << levels);
+  snprintf(c.last_path, sizeof c.last_path, levels ? "strassen:%d" : "m4rm", levels);
+
+  size_t const need = Workspace::bytes_for(mp, lp) + Workspace::bytes_for(lp, np) + Workspace::bytes_for(mp, np) +
+                      strassen_workspace_bytes(mp, lp, np, levels);
+  c.ws.reserve(need);
+  cudaStream_t s = c.stream;
+  DView dA = c.ws.alloc(mp, lp), dB = c.ws.alloc(lp, np), dC = c.ws.alloc(mp, np);
+  zero_async(dA, s);
+  zero_async(dB, s);
+  upload(dA, A, s);
+  upload(dB, B, s);
+  if (!clear) {
+    zero_async(dC, s);
+    upload(dC, C, s);
+  }
+  strassen_mul(dC, dA, dB, levels, clear, c.ws, s);
+  download(C, dC, s, c.host_tmp);
+  M4B_CUDA(cudaStreamSynchronize(s));
+  c.ws.release(0);
+}
+
+mzd_t *checked(char const *who, mzd_t *C, mzd_t const *A, mzd_t const *B) {
+  if (A->ncols != B->nrows) die("%s: A ncols (%d) need to match B nrows (%d).\n", who, A->ncols, B->nrows);
+  if (C == NULL) return alloc_result(A->nrows, B->ncols);
+  if (C->nrows != A->nrows || C->ncols != B->ncols)
+    die("%s: C (%d x %d) has wrong dimensions, expected (%d x %d)\n", who, C->nrows, C->ncols, A->nrows, B->ncols);
+  return C;
+}
+
+DView as_view(m4ri_b200_dmat const *M) { return DView{M->data, M->pitch, M->nrows, M->ncols}; }
+
+void device_product(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int levels, bool clear,
+                    cudaStream_t s) {
+  Ctx &c = ctx();
+  if (A->ncols != B->nrows || C->nrows != A->nrows || C->ncols != B->ncols)
+    die("m4ri_b200_dmul: dimension mismatch (%dx%d) * (%dx%d) -> (%dx%d)\n", A->nrows, A->ncols, B->nrows, B->ncols,
+        C->nrows, C->ncols);
+  int const m = A->nrows, l = A->ncols, n = B->ncols;
+  if (m == 0 || n == 0) return;
+  if (l == 0) {
+    if (clear) launch_zero(as_view(C), s);
+    return;
+  }
+  snprintf(c.last_path, sizeof c.last_path, levels ? "strassen:%d" : "m4rm", levels);
+  int const mp = round_up(m, 1 << levels), lp = round_up(l, 128 << levels), np = round_up(n, 128 << levels);
+  bool const pad = levels > 0 && (mp != m || lp != l || np != n);
+  if (!pad) {
+    c.ws.reserve(strassen_workspace_bytes(m, l, n, levels));
+    strassen_mul(as_view(C), as_view(A), as_view(B), levels, clear, c.ws, s);
+    return;
+  }
+  c.ws.reserve(Workspace::bytes_for(mp, lp) + Workspace::bytes_for(lp, np) + Workspace::bytes_for(mp, np) +
+               strassen_workspace_bytes(mp, lp, np, levels));
+  DView dA = c.ws.alloc(mp, lp), dB = c.ws.alloc(lp, np), dC = c.ws.alloc(mp, np);
+  zero_async(dA, s);
+  zero_async(dB, s);
+  launch_copy(dA.sub(0, 0, m, l), as_view(A), s);
+  launch_copy(dB.sub(0, 0, l, n), as_view(B), s);
+  if (!clear) {
+    zero_async(dC, s);
+    launch_copy(dC.sub(0, 0, m, n), as_view(C), s);
+  }
+  strassen_mul(dC, dA, dB, levels, clear, c.ws, s);
+  launch_copy(as_view(C), dC.sub(0, 0, m, n), s);
+  c.ws.release(0);   // stream-ordered reuse: later work on `s` runs after these kernels
+}
+
+}  // namespace
+}  // namespace m4b
+
+using namespace m4b;
+
+extern "C" {
+
+// ---- Part 1: reference-named entry points ----------------------------------------------
+
+mzd_t *mzd_mul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  if (A->ncols != B->nrows) die("mzd_mul: A ncols (%d) need to match B nrows (%d).\n", A->ncols, B->nrows);
+  cutoff = norm_cutoff(cutoff, "mzd_mul");
+  C = checked("mzd_mul", C, A, B);
+  host_product(C, A, B, cutoff, true, true);
+  return C;
+}
+
+mzd_t *mzd_addmul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  if (A->ncols != B->nrows) die("mzd_addmul: A ncols (%d) need to match B nrows (%d).\n", A->ncols, B->nrows);
+  cutoff = norm_cutoff(cutoff, "mzd_addmul");
+  C = checked("mzd_addmul", C, A, B);
+  if (A->nrows == 0 || A->ncols == 0 || B->ncols == 0) return C;   // strassen.c:692-695
+  host_product(C, A, B, cutoff, false, true);
+  return C;
+}
+
+mzd_t *_mzd_addmul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  host_product(C, A, B, cutoff < 64 ? 64 : cutoff, false, true);
+  return C;
+}
+
+mzd_t *_mzd_mul_even(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  host_product(C, A, B, cutoff < 64 ? 64 : cutoff, true, true);
+  return C;
+}
+
+mzd_t *_mzd_addmul_even(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  host_product(C, A, B, cutoff < 64 ? 64 : cutoff, false, true);
+  return C;
+}
+
+mzd_t *_mzd_mul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k, int clear) {
+  (void)k;   // any table width gives the same bits; the kernel's k is fixed at 8
+  host_product(C, A, B, 0, clear != 0, false);
+  return C;
+}
+
+mzd_t *mzd_mul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k) {
+  C = checked("mzd_mul_m4rm", C, A, B);
+  return _mzd_mul_m4rm(C, A, B, k, 1);
+}
+
+mzd_t *mzd_addmul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k) {
+  // the reference dereferences C before its NULL test (brilliantrussian.c:1018 vs 1022); we test first
+  if (C != NULL && (C->ncols == 0 || C->nrows == 0)) return C;
+  C = checked("mzd_addmul_m4rm", C, A, B);
+  return _mzd_mul_m4rm(C, A, B, k, 0);
+}
+
+mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) { return mzd_mul(C, A, B, cutoff); }
+mzd_t *mzd_addmul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) { return mzd_addmul(C, A, B, cutoff); }
+
+// ---- Part 2: extension API ------------------------------------------------------------------
+
+int m4ri_b200_version(void) { return 100; }
+
+int m4ri_b200_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+  return count;
+}
+
+void m4ri_b200_set_device(int device) {
+  if (g.ready && g.device != device) {
+    g.ws.destroy();
+    cudaStreamDestroy(g.stream);
+    g.ready = false;
+  }
+  g.device = device;
+}
+
+void m4ri_b200_set_num_devices(int n) { g.num_devices = n < 1 ? 1 : n; }
+void m4ri_b200_set_default_cutoff(int cutoff) { g.default_cutoff = cutoff > 0 ? cutoff : kBuiltinCutoff; }
+int  m4ri_b200_get_default_cutoff(void) { return g.default_cutoff ? g.default_cutoff : kBuiltinCutoff; }
+
+void m4ri_b200_release(void) {
+  if (!g.ready) return;
+  cudaStreamSynchronize(g.stream);
+  g.ws.destroy();
+}
+
+char const *m4ri_b200_last_path(void) { return g.last_path; }
+uint64_t    m4ri_b200_kernel_launches(void) { return g_kernel_launches; }
+
+mzd_t *m4ri_b200_mzd_init(rci_t r, rci_t c) {
+  mzd_t *M = static_cast<mzd_t *>(malloc(sizeof(mzd_t)));
+  fill_header(M, r, c);
+  M->rowstride = M->width + (M->width & 1);
+  if (r && c) {
+    size_t const bytes = (size_t)r * (size_t)M->rowstride * sizeof(word);
+    if (posix_memalign(reinterpret_cast<void **>(&M->data), 64, bytes)) die("m4ri_b200_mzd_init: out of memory\n");
+    memset(M->data, 0, bytes);
+  }
+  return M;
+}
+
+mzd_t *m4ri_b200_mzd_init_window(mzd_t *P, rci_t lowr, rci_t lowc, rci_t highr, rci_t highc) {
+  if (lowc % 64) die("m4ri_b200_mzd_init_window: lowc must be a multiple of 64\n");
+  mzd_t *W = static_cast<mzd_t *>(malloc(sizeof(mzd_t)));
+  rci_t nr = highr - lowr;
+  if (P->nrows - lowr < nr) nr = P->nrows - lowr;
+  fill_header(W, nr, highc - lowc);
+  W->flags |= kFlagWindow;
+  W->rowstride = P->rowstride;
+  W->data = P->data + (int64_t)lowr * P->rowstride + lowc / 64;
+  return W;
+}
+
+void m4ri_b200_mzd_free(mzd_t *M) {
+  if (!M) return;
+  if (!(M->flags & kFlagWindow)) free(M->data);
+  free(M);
+}
+
+m4ri_b200_dmat *m4ri_b200_dmat_alloc(rci_t nrows, rci_t ncols) {
+  ctx();
+  m4ri_b200_dmat *M = static_cast<m4ri_b200_dmat *>(calloc(1, sizeof *M));
+  M->nrows = nrows;
+  M->ncols = ncols;
+  M->pitch = Workspace::pitch_for(ncols);
+  M->owner = 1;
+  size_t const bytes = (size_t)nrows * (size_t)M->pitch * 8;
+  if (bytes) {
+    M4B_CUDA(cudaMalloc(&M->data, bytes));
+    M4B_CUDA(cudaMemset(M->data, 0, bytes));
+  }
+  return M;
+}
+
+m4ri_b200_dmat *m4ri_b200_dmat_wrap(void *device_ptr, int64_t pitch_words, rci_t nrows, rci_t ncols) {
+  if (((uintptr_t)device_ptr & 15) || (pitch_words & 1) || pitch_words < Workspace::pitch_for(ncols))
+    die("m4ri_b200_dmat_wrap: pointer must be 16-byte aligned and pitch even and >= %lld words\n",
+        (long long)Workspace::pitch_for(ncols));
+  m4ri_b200_dmat *M = static_cast<m4ri_b200_dmat *>(calloc(1, sizeof *M));
+  M->data = static_cast<word *>(device_ptr);
+  M->pitch = pitch_words;
+  M->nrows = nrows;
+  M->ncols = ncols;
+  return M;
+}
+
+void m4ri_b200_dmat_free(m4ri_b200_dmat *M) {
+  if (!M) return;
+  if (M->owner && M->data) cudaFree(M->data);
+  free(M);
+}
+
+void m4ri_b200_upload(m4ri_b200_dmat *dst, mzd_t const *src, void *stream) {
+  if (dst->nrows != src->nrows || dst->ncols != src->ncols) die("m4ri_b200_upload: dimension mismatch\n");
+  upload(as_view(dst), src, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+  if (!stream) M4B_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
+void m4ri_b200_download(mzd_t *dst, m4ri_b200_dmat const *src, void *stream) {
+  if (dst->nrows != src->nrows || dst->ncols != src->ncols) die("m4ri_b200_download: dimension mismatch\n");
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
+  download(dst, as_view(src), s, ctx().host_tmp);
+  M4B_CUDA(cudaStreamSynchronize(s));
+}
+
+void m4ri_b200_sync(void *stream) {
+  M4B_CUDA(cudaStreamSynchronize(stream ? static_cast<cudaStream_t>(stream) : ctx().stream));
+}
+
+void m4ri_b200_dmul_m4rm(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int clear, void *stream) {
+  device_product(C, A, B, 0, clear != 0, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+}
+
+void m4ri_b200_dmul(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int cutoff, int clear,
+                    void *stream) {
+  cutoff = norm_cutoff(cutoff, "m4ri_b200_dmul");
+  int const levels = A->ncols > 0 ? strassen_levels(A->nrows, A->ncols, B->ncols, cutoff) : 0;
+  device_product(C, A, B, levels, clear != 0, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+}
+
+void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {
+  if (A->nrows != B->nrows || A->ncols != B->ncols || C->nrows != A->nrows || C->ncols != A->ncols)
+    die("m4ri_b200_dadd: dimension mismatch\n");
+  launch_xor(as_view(C), as_view(A), as_view(B), stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+}
+
+}  // extern "C"

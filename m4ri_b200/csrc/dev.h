@@ -1,0 +1,56 @@
+// dev.h — internal declarations shared by the CUDA kernels and the host scheduler.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/m4ri_b200.h"
+
+namespace m4b {
+
+// m4ri_die convention (m4ri/misc.c:36-42): message to stderr, then abort().
+[[noreturn]] void die(char const *fmt, ...);
+
+#define M4B_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      ::m4b::die("m4ri_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, \
+                 __LINE__, cudaGetErrorString(e_));                                          \
+  } while (0)
+
+// A view of a device-resident bit-packed matrix.  Invariants: data 16-byte aligned,
+// pitch (64-bit words) even, all bits in columns [ncols, 64*pitch) of every row that
+// belong to THIS allocation are zero (sub-views of Strassen only ever split on
+// 128-bit boundaries, so a view's "padding" is never someone else's data unless
+// ncols % 128 == 0).
+struct DView {
+  word   *data;
+  int64_t pitch;
+  int     nrows;
+  int     ncols;
+  DView sub(int r0, int c0, int r1, int c1) const {  // c0 % 128 == 0
+    return DView{data + (int64_t)r0 * pitch + c0 / 64, pitch, r1 - r0, c1 - c0};
+  }
+};
+
+extern unsigned long long g_kernel_launches;  // counted by every launcher in this library
+
+// ---- leaf: C ^= A*B (M4RM, stream-K persistent kernel) -------------------------------
+// C must already hold the addend (zeros for a plain product).
+void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream);
+int  m4rm_num_sms();
+
+// ---- element-wise helpers on views (all 128-bit vectorised) --------------------------
+void launch_xor(DView C, DView A, DView B, cudaStream_t stream);        // C = A ^ B
+void launch_zero(DView C, cudaStream_t stream);                          // C = 0
+void launch_copy(DView C, DView A, cudaStream_t stream);                 // C = A
+void launch_mask_excess(DView C, cudaStream_t stream);                   // clear bits >= ncols of last word(s)
+
+// ---- host scheduler ------------------------------------------------------------------
+struct Workspace;  // bump allocator over one cached device slab
+int  strassen_levels(int m, int k, int n, int cutoff);
+void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s);
+
+}  // namespace m4b

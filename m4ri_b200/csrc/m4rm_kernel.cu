@@ -1,0 +1,372 @@
+// m4rm_kernel.cu — the M4RM ("Method of the Four Russians" multiplication) leaf for sm_100a.
+//
+// Replaces the reference's _mzd_mul_m4rm hot loops (m4ri/brilliantrussian.c:1107-1178):
+//   mzd_make_table  (brilliantrussian.c:163-211)  -> build_tables(): 2^8-entry Gray-code
+//                                                    tables built directly in shared memory
+//   mzd_read_bits   (mzd.h:892-901)               -> byte extraction from the TMA-staged A slab
+//   _mzd_combine_8  (xor_template.h, xor.h:96-122) -> LDS.128 table-row lookups XORed into a
+//                                                    register-resident C tile
+//
+// B200 design (not a translation of the CPU code):
+//   * One persistent CTA per SM.  The (C-tile x K-slab) iteration space is split evenly over
+//     the CTAs ("stream-K"); because GF(2) accumulation is XOR, partial tiles are merged into
+//     C with red.global.xor — exact, order independent, no second pass.
+//   * C tile = TM x 1024 bits lives in registers for the whole K range of a segment
+//     (C is touched once per segment instead of once per 64 columns of A as on the CPU).
+//   * A table row is exactly 128 B = all 32 banks, so the 8 lanes that own one C row fetch one
+//     whole row with a conflict-free LDS.128; one warp instruction serves 4 C rows.
+//   * k = 8 bits per table, 2 tables (16 columns of A) per step, tables double buffered: the
+//     tables for step i+1 are built (Gray-code walk, one STS.128 per entry, no table reads)
+//     while step i's lookups run; one __syncthreads per step.
+//   * A (TM x 128 bit) and B (128 x 1024 bit) slabs arrive by TMA (cp.async.bulk.tensor.2d)
+//     into a 2-deep ring guarded by mbarriers; out-of-range rows/columns are zero-filled by
+//     the TMA unit, which is what makes ragged m / l / n edges free.
+//
+// Binding resource: shared-memory bandwidth (128 B/clk/SM): per step and per warp 32 lookups
+// (4 wavefronts each) + 8 table stores (4 each) + 8 B-row loads + 8 A loads = 176 wavefronts
+// for 2*16*64*1024 bit-ops.  See DESIGN.md for the roofline derived from this.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "dev.h"
+
+namespace m4b {
+
+namespace {
+
+constexpr int kTileBits   = 1024;               // C tile width in bits (one table row = 128 B)
+constexpr int kRowBytes   = kTileBits / 8;      // 128
+constexpr int kTableBytes = 256 * kRowBytes;    // k = 8 -> 32 KB per table
+constexpr int kStepBufBytes = 2 * kTableBytes;  // two tables per step
+constexpr int kSlabBits   = 128;                // K extent of one TMA slab
+constexpr int kStepsPerSlab = kSlabBits / 16;   // 8 steps of 16 A-columns
+constexpr int kBSlabBytes = kSlabBits * kRowBytes;  // 16 KB
+
+struct Params {
+  unsigned long long *C;
+  long long pitchC;     // words
+  int m;                // rows of A / C
+  int nwordsC;          // 64-bit words per C row that may be written
+  int tiles_m;
+  int tiles_n;
+  int slabs;            // ceil(l / 128)
+  long long total_units;  // tiles_m * tiles_n * slabs
+};
+
+__device__ __forceinline__ uint32_t smem_u32(void const *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, CUtensorMap const *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_xor64(unsigned long long *p, uint32_t lo, uint32_t hi) {
+  unsigned long long v = (static_cast<unsigned long long>(hi) << 32) | lo;
+  asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void xor4(uint4 &a, uint4 const &b) { a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w; }
+__device__ __forceinline__ void xor4m(uint4 &a, uint4 const &b, uint32_t m) {
+  a.x ^= b.x & m; a.y ^= b.y & m; a.z ^= b.z & m; a.w ^= b.w & m;
+}
+
+__host__ __device__ constexpr int ctz_c(int v) { return (v & 1) ? 0 : 1 + ctz_c(v >> 1); }
+
+template <int TM, int NT>
+struct Cfg {
+  static constexpr int kWarps      = NT / 32;
+  static constexpr int kRowsPerWarp = TM / kWarps;
+  static constexpr int R           = kRowsPerWarp / 4;   // C rows held per thread
+  static constexpr int kGroups     = NT / 8;             // 8-lane groups that build table entries
+  static constexpr int kEntries    = 512 / kGroups;      // entries each group builds per step
+  static constexpr int kGrayBits   = kEntries == 8 ? 3 : (kEntries == 16 ? 4 : (kEntries == 4 ? 2 : -1));
+  static constexpr int kASlabBytes = TM * 16;
+  static constexpr int kABoxRows   = TM < 256 ? TM : 256;
+  static constexpr int kOffTables  = 0;
+  static constexpr int kOffA       = 2 * kStepBufBytes;
+  static constexpr int kOffB       = kOffA + 2 * kASlabBytes;
+  static constexpr int kOffBar     = kOffB + 2 * kBSlabBytes;
+  static constexpr int kSmemBytes  = kOffBar + 64;
+  static constexpr uint32_t kSlabTxBytes = kASlabBytes + kBSlabBytes;
+  static_assert(kGrayBits > 0, "unsupported thread count");
+  static_assert(R >= 1 && kRowsPerWarp % 4 == 0, "bad tile shape");
+};
+
+// Build the two 256-entry tables of one step from 16 rows of the B slab.
+// Thread (g = tid/8, c = tid%8): table t = g / (groups/2), high index bits h, 16-byte column
+// chunk c.  base = XOR of the B rows selected by h; the low kGrayBits index bits are walked in
+// reflected Gray order so each further entry costs one 128-bit XOR and one STS.128 —
+// the same trick as mzd_make_table, but per thread and without reading the table back.
+template <int TM, int NT>
+__device__ __forceinline__ void build_tables(uint32_t tbuf, uint32_t brows16, int tid) {
+  using C = Cfg<TM, NT>;
+  constexpr int GB = C::kGrayBits;
+  int const g = tid >> 3, c = tid & 7;
+  int const t = g / (C::kGroups / 2);
+  int const h = g % (C::kGroups / 2);                       // index bits GB..7
+  uint32_t const src = brows16 + (t * 8) * kRowBytes + c * 16;
+  uint4 low[GB];
+#pragma unroll
+  for (int b = 0; b < GB; ++b) low[b] = lds128(src + b * kRowBytes);
+  uint4 e = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int b = GB; b < 8; ++b) {
+    uint4 v = lds128(src + b * kRowBytes);
+    xor4m(e, v, 0u - ((h >> (b - GB)) & 1u));
+  }
+  uint32_t const dst = tbuf + t * kTableBytes + (h << GB) * kRowBytes + c * 16;
+  sts128(dst, e);
+#pragma unroll
+  for (int i = 1; i < (1 << GB); ++i) {
+    int const flip = ctz_c(i);                 // bit that changes between gray(i-1) and gray(i)
+    xor4(e, low[flip]);
+    sts128(dst + (i ^ (i >> 1)) * kRowBytes, e);
+  }
+}
+
+template <int TM, int NT>
+__global__ void __launch_bounds__(NT, 1)
+m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p) {
+  using C = Cfg<TM, NT>;
+  constexpr int R = C::R;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint32_t const sbase = smem_u32(smem);
+  uint32_t const sTab = sbase + C::kOffTables;
+  uint32_t const sA   = sbase + C::kOffA;
+  uint32_t const sB   = sbase + C::kOffB;
+  uint32_t const sBar = sbase + C::kOffBar;     // two 8-byte mbarriers
+
+  int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int const q = lane >> 3, c = lane & 7;
+
+  if (tid == 0) {
+    mbar_init(sBar, 1);
+    mbar_init(sBar + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  long long const u_begin = p.total_units * (long long)blockIdx.x / gridDim.x;
+  long long const u_end   = p.total_units * (long long)(blockIdx.x + 1) / gridDim.x;
+  uint32_t parity0 = 0, parity1 = 0;             // phase of each ring slot
+
+  uint32_t const a_row_off = (warp * C::kRowsPerWarp + q) * 16;   // first A row of this lane group
+  uint32_t const lane_off  = c * 16;
+
+  for (long long u = u_begin; u < u_end;) {
+    int const tile  = (int)(u / p.slabs);
+    int const s0    = (int)(u % p.slabs);
+    int nseg        = p.slabs - s0;
+    if ((long long)nseg > u_end - u) nseg = (int)(u_end - u);
+    int const tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+    int const row0 = tm * TM;
+
+    auto issue = [&](int i) {                     // thread 0: TMA for slab s0+i into ring slot i&1
+      uint32_t const slot = i & 1;
+      uint32_t const bar  = sBar + 8 * slot;
+      mbar_expect_tx(bar, C::kSlabTxBytes);
+#pragma unroll
+      for (int part = 0; part < TM / C::kABoxRows; ++part)
+        tma_load_2d(sA + slot * C::kASlabBytes + part * C::kABoxRows * 16, &mapA, (s0 + i) * 4,
+                    row0 + part * C::kABoxRows, bar);
+      tma_load_2d(sB + slot * kBSlabBytes, &mapB, tn * 32, (s0 + i) * kSlabBits, bar);
+    };
+
+    if (tid == 0) {
+      issue(0);
+      if (nseg > 1) issue(1);
+    }
+
+    uint4 acc[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = make_uint4(0, 0, 0, 0);
+
+    // rows of this warp that exist: lookups for j >= jmax are skipped (warp-uniform)
+    int jmax = (p.m - row0 - warp * C::kRowsPerWarp + 3) >> 2;
+    jmax = jmax < 0 ? 0 : (jmax > R ? R : jmax);
+
+    mbar_wait(sBar, parity0);
+    parity0 ^= 1;
+    build_tables<TM, NT>(sTab, sB, tid);
+    __syncthreads();
+
+    for (int i = 0; i < nseg; ++i) {
+      uint32_t const slot = i & 1;
+      uint32_t const aS = sA + slot * C::kASlabBytes + a_row_off;
+      uint32_t const bS = sB + slot * kBSlabBytes;
+#pragma unroll 1
+      for (int pr = 0; pr < kStepsPerSlab / 2; ++pr) {
+        uint32_t aw[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) aw[j] = lds32(aS + j * 64 + pr * 4);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          int const step = pr * 2 + sub;
+          uint32_t const tcur = sTab + sub * kStepBufBytes;          // step parity == sub
+          uint32_t const tnext = sTab + (sub ^ 1) * kStepBufBytes;
+          // ---- build tables for the next step into the other buffer ----
+          if (step < kStepsPerSlab - 1) {
+            build_tables<TM, NT>(tnext, bS + (step + 1) * 16 * kRowBytes, tid);
+          } else if (i + 1 < nseg) {
+            if (slot == 0) { mbar_wait(sBar + 8, parity1); parity1 ^= 1; }
+            else           { mbar_wait(sBar, parity0);     parity0 ^= 1; }
+            build_tables<TM, NT>(tnext, sB + (slot ^ 1) * kBSlabBytes, tid);
+          }
+          // ---- lookups: acc[j] ^= T0[a byte 2*sub] ^ T1[a byte 2*sub+1] ----
+          uint32_t const t0 = tcur + lane_off, t1 = tcur + kTableBytes + lane_off;
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            if (j < jmax) {
+              uint32_t const i0 = __byte_perm(aw[j], 0, 0x4440 + 2 * sub);
+              uint32_t const i1 = __byte_perm(aw[j], 0, 0x4441 + 2 * sub);
+              uint4 const v0 = lds128(t0 + i0 * kRowBytes);
+              uint4 const v1 = lds128(t1 + i1 * kRowBytes);
+              acc[j].x ^= v0.x ^ v1.x;
+              acc[j].y ^= v0.y ^ v1.y;
+              acc[j].z ^= v0.z ^ v1.z;
+              acc[j].w ^= v0.w ^ v1.w;
+            }
+          }
+          __syncthreads();
+        }
+      }
+      // ring slot `slot` is free again: refill it with slab i+2
+      if (tid == 0 && i + 2 < nseg) issue(i + 2);
+    }
+
+    // ---- merge the partial tile into C (exact: XOR is associative and commutative) ----
+    {
+      int const wcol = tn * (kTileBits / 64) + c * 2;
+      int const rbase = row0 + warp * C::kRowsPerWarp + q;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        int const row = rbase + 4 * j;
+        if (row < p.m) {
+          unsigned long long *dst = p.C + (long long)row * p.pitchC + wcol;
+          if (wcol < p.nwordsC) red_xor64(dst, acc[j].x, acc[j].y);
+          if (wcol + 1 < p.nwordsC) red_xor64(dst + 1, acc[j].z, acc[j].w);
+        }
+      }
+    }
+    // all table/slab reads of this segment are complete before the next segment's prologue
+    __syncthreads();
+    u += nseg;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    M4B_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr));
+    if (!sym || qr != cudaDriverEntryPointSuccess) die("m4ri_b200: cuTensorMapEncodeTiled not available from the driver\n");
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2D map over u32 elements of a bit-packed view: dim0 = 32-bit words of the (128-bit padded)
+// row, dim1 = rows.  Reads outside [dim0) x [dim1) return zeros.
+CUtensorMap make_map(DView V, int box_w32, int box_rows) {
+  CUtensorMap map;
+  cuuint64_t dims[2]    = {(cuuint64_t)((V.ncols + 127) / 128) * 4, (cuuint64_t)V.nrows};
+  cuuint64_t strides[1] = {(cuuint64_t)V.pitch * 8};
+  cuuint32_t box[2]     = {(cuuint32_t)box_w32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, V.data, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    die("m4ri_b200: cuTensorMapEncodeTiled failed (%d) for view %p pitch %lld %dx%d\n", (int)r, (void *)V.data,
+        (long long)V.pitch, V.nrows, V.ncols);
+  return map;
+}
+
+template <int TM, int NT>
+void launch_variant(DView Cv, DView A, DView B, cudaStream_t stream) {
+  using C = Cfg<TM, NT>;
+  static bool configured = false;
+  auto kern = m4rm_streamk_kernel<TM, NT>;
+  if (!configured) {
+    M4B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  Params p;
+  p.C = reinterpret_cast<unsigned long long *>(Cv.data);
+  p.pitchC = Cv.pitch;
+  p.m = A.nrows;
+  p.nwordsC = (Cv.ncols + 63) / 64;
+  p.tiles_m = (A.nrows + TM - 1) / TM;
+  p.tiles_n = (B.ncols + kTileBits - 1) / kTileBits;
+  p.slabs = (A.ncols + kSlabBits - 1) / kSlabBits;
+  p.total_units = (long long)p.tiles_m * p.tiles_n * p.slabs;
+  CUtensorMap mapA = make_map(A, 4, C::kABoxRows);
+  CUtensorMap mapB = make_map(B, 32, kSlabBits);
+  long long grid = m4rm_num_sms();
+  if (grid > p.total_units) grid = p.total_units;
+  kern<<<(unsigned)grid, NT, C::kSmemBytes, stream>>>(mapA, mapB, p);
+  M4B_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+
+}  // namespace
+
+int m4rm_num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    M4B_CUDA(cudaGetDevice(&dev));
+    M4B_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return sms;
+}
+
+void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) {
+  if (A.nrows <= 0 || A.ncols <= 0 || B.ncols <= 0) return;   // empty product: C unchanged
+  if (A.nrows <= 256)
+    launch_variant<256, 256>(C, A, B, stream);
+  else
+    launch_variant<1024, 512>(C, A, B, stream);
+}
+
+}  // namespace m4b

@@ -1,0 +1,112 @@
+// strassen.cu — host-side Strassen-Winograd scheduler over device views.
+//
+// Device counterpart of _mzd_mul_even / _mzd_addmul_even (m4ri/strassen.c:41-208, 367-526):
+// the same Winograd/Bodrato operation sequences, but every "+" is one HBM-bound XOR kernel and
+// every leaf product is one persistent M4RM launch, all enqueued on a single stream (the stream
+// order is the dependency order, so the host never synchronises inside the recursion).
+//
+// Differences from the CPU scheduler, none of which can change a bit of the result:
+//   * The caller pads the operands with zeros to multiples of 2^levels rows and 128*2^levels
+//     columns (capi.cu), so every level halves exactly on 128-bit boundaries and there are no
+//     edge strips (strassen.c:171-204) and no window copies (strassen.c:54-62).
+//   * The recursion depth is fixed up front by strassen_levels(), which applies the
+//     reference's own leaf test `3*dim < 4*cutoff` (strassen.c:39,51) level by level.
+//   * Temporaries come from a bump allocator over one cached device slab (no malloc per node).
+#include "dev.h"
+#include "workspace.h"
+
+namespace m4b {
+
+static inline bool closer(int a, int cutoff) { return 3LL * a < 4LL * cutoff; }
+
+int strassen_levels(int m, int k, int n, int cutoff) {
+  int levels = 0;
+  while (!(closer(m, cutoff) || closer(k, cutoff) || closer(n, cutoff)) && m >= 2 && k >= 256 && n >= 256) {
+    m = (m + 1) / 2;
+    k = (k + 1) / 2;
+    n = (n + 1) / 2;
+    ++levels;
+  }
+  return levels;
+}
+
+size_t strassen_workspace_bytes(int m, int k, int n, int levels) {
+  size_t total = 0;
+  for (int lv = 0; lv < levels; ++lv) {
+    m /= 2; k /= 2; n /= 2;
+    total += Workspace::bytes_for(m, k) + Workspace::bytes_for(k, n) + Workspace::bytes_for(m, n);
+  }
+  return total;
+}
+
+void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s) {
+  if (C.nrows <= 0 || C.ncols <= 0) return;
+  if (levels == 0) {
+    if (clear) launch_zero(C, s);
+    launch_m4rm(C, A, B, s);
+    return;
+  }
+  int const m2 = A.nrows / 2, k2 = A.ncols / 2, n2 = B.ncols / 2;
+  DView const a11 = A.sub(0, 0, m2, k2), a12 = A.sub(0, k2, m2, 2 * k2);
+  DView const a21 = A.sub(m2, 0, 2 * m2, k2), a22 = A.sub(m2, k2, 2 * m2, 2 * k2);
+  DView const b11 = B.sub(0, 0, k2, n2), b12 = B.sub(0, n2, k2, 2 * n2);
+  DView const b21 = B.sub(k2, 0, 2 * k2, n2), b22 = B.sub(k2, n2, 2 * k2, 2 * n2);
+  DView const c11 = C.sub(0, 0, m2, n2), c12 = C.sub(0, n2, m2, 2 * n2);
+  DView const c21 = C.sub(m2, 0, 2 * m2, n2), c22 = C.sub(m2, n2, 2 * m2, 2 * n2);
+
+  size_t const mark = ws.mark();
+  int const lv = levels - 1;
+  if (clear) {
+    // C = A*B, 7 products, 15 adds (strassen.c:111-150)
+    DView X = ws.alloc(m2, k2), Y = ws.alloc(k2, n2), P = ws.alloc(m2, n2);
+    launch_xor(Y, b22, b12, s);
+    launch_xor(X, a22, a12, s);
+    strassen_mul(c21, X, Y, lv, true, ws, s);
+    launch_xor(X, a22, a21, s);
+    launch_xor(Y, b22, b21, s);
+    strassen_mul(c22, X, Y, lv, true, ws, s);
+    launch_xor(Y, Y, b12, s);
+    launch_xor(X, X, a12, s);
+    strassen_mul(c11, X, Y, lv, true, ws, s);
+    launch_xor(X, X, a11, s);
+    strassen_mul(c12, X, b12, lv, true, ws, s);
+    launch_xor(c12, c12, c22, s);
+    strassen_mul(P, a12, b21, lv, true, ws, s);
+    launch_xor(c11, c11, P, s);
+    launch_xor(c12, c11, c12, s);
+    launch_xor(c11, c21, c11, s);
+    launch_xor(Y, Y, b11, s);
+    strassen_mul(c21, a21, Y, lv, true, ws, s);
+    launch_xor(c21, c11, c21, s);
+    launch_xor(c22, c22, c11, s);
+    strassen_mul(c11, a11, b11, lv, true, ws, s);
+    launch_xor(c11, c11, P, s);
+  } else {
+    // C ^= A*B, 7 products, 14 adds (strassen.c:436-466)
+    DView S = ws.alloc(m2, k2), T = ws.alloc(k2, n2), U = ws.alloc(m2, n2);
+    launch_xor(S, a22, a21, s);
+    launch_xor(T, b22, b21, s);
+    strassen_mul(U, S, T, lv, true, ws, s);
+    launch_xor(c22, U, c22, s);
+    launch_xor(c12, U, c12, s);
+    strassen_mul(U, a12, b21, lv, true, ws, s);
+    launch_xor(c11, U, c11, s);
+    strassen_mul(c11, a11, b11, lv, false, ws, s);
+    launch_xor(S, S, a12, s);
+    launch_xor(T, T, b12, s);
+    strassen_mul(U, S, T, lv, false, ws, s);
+    launch_xor(c12, c12, U, s);
+    launch_xor(S, a11, S, s);
+    strassen_mul(c12, S, b12, lv, false, ws, s);
+    launch_xor(T, b11, T, s);
+    strassen_mul(c21, a21, T, lv, false, ws, s);
+    launch_xor(S, a22, a12, s);
+    launch_xor(T, b22, b12, s);
+    strassen_mul(U, S, T, lv, false, ws, s);
+    launch_xor(c21, c21, U, s);
+    launch_xor(c22, c22, U, s);
+  }
+  ws.release(mark);
+}
+
+}  // namespace m4b
