@@ -23,7 +23,7 @@ MZD_FLAG_WINDOWED = 0x4        # m4ri/mzd.h:150
 
 
 class MzdT(ctypes.Structure):
-    """64-byte ``mzd_t`` header (m4ri/mzd.h:68-99); shared by reference, oracle and product."""
+    """64-byte ``mzd_t`` header (m4ri/mzd.h:68-99); the one layout every libm4ri-compatible library uses."""
 
     _fields_ = [
         ("nrows", c_int),

@@ -11,7 +11,7 @@
  *                               345-365 / 675-700 (entry points)
  * Written from the behavioural description, not copied: no SSE2, no OpenMP, no
  * allocator caches.  Results are pinned bit-for-bit against the compiled
- * reference by tests/test_oracle_vs_ref.py.
+ * reference by tests/test_oracle.py.
  */
 #define _DEFAULT_SOURCE
 #include "m4rm_oracle.h"
@@ -89,6 +89,7 @@ orc_word orc_random_word(void) { /* three 31-bit draws (misc.c:65-69) */
 }
 
 void orc_randomize(orc_mzd *M) { /* row-major, one draw per word, last word merged under mask */
+  if (!M->width) return;
   for (orc_rci i = 0; i < M->nrows; ++i) {
     orc_word *row = rowp(M, i);
     for (orc_wi j = 0; j + 1 < M->width; ++j) row[j] = orc_random_word();
@@ -99,6 +100,7 @@ void orc_randomize(orc_mzd *M) { /* row-major, one draw per word, last word merg
 
 int orc_equal(orc_mzd const *A, orc_mzd const *B) { /* valid bits only (mzd.c:1314-1331) */
   if (A->nrows != B->nrows || A->ncols != B->ncols) return 0;
+  if (!A->width) return 1;
   for (orc_rci i = 0; i < A->nrows; ++i) {
     orc_word const *a = rowp(A, i), *b = rowp(B, i);
     for (orc_wi j = 0; j + 1 < A->width; ++j)

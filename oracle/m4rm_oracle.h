@@ -6,7 +6,7 @@
  * bench.py's cpu_baseline leg can check the CUDA product path; nothing under
  * m4ri_b200/ may include, link or call it.
  *
- * Parity status: PINNED — tests/test_oracle_vs_ref.py checks every function
+ * Parity status: PINNED — tests/test_oracle.py checks every function
  * here bit-for-bit against the unmodified reference compiled into
  * oracle/_ref/libm4ri_ref.so on the reference's own test shape list
  * (tests/test_multiplication.c:251-322) and against the committed fixtures in
