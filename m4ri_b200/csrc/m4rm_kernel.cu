@@ -104,8 +104,6 @@ __device__ __forceinline__ void xor4m(uint4 &a, uint4 const &b, uint32_t m) {
   a.x ^= b.x & m; a.y ^= b.y & m; a.z ^= b.z & m; a.w ^= b.w & m;
 }
 
-__host__ __device__ constexpr int ctz_c(int v) { return (v & 1) ? 0 : 1 + ctz_c(v >> 1); }
-
 template <int TM, int NT>
 struct Cfg {
   static constexpr int kWarps      = NT / 32;
@@ -152,8 +150,8 @@ __device__ __forceinline__ void build_tables(uint32_t tbuf, uint32_t brows16, in
   sts128(dst, e);
 #pragma unroll
   for (int i = 1; i < (1 << GB); ++i) {
-    int const flip = ctz_c(i);                 // bit that changes between gray(i-1) and gray(i)
-    xor4(e, low[flip]);
+    // bit that changes between gray(i-1) and gray(i) = ctz(i); spelled so it folds after unrolling
+    xor4(e, low[(i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : 3]);
     sts128(dst + (i ^ (i >> 1)) * kRowBytes, e);
   }
 }
@@ -216,10 +214,6 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
     for (int j = 0; j < R; ++j) acc[j] = make_uint4(0, 0, 0, 0);
 
-    // rows of this warp that exist: lookups for j >= jmax are skipped (warp-uniform)
-    int jmax = (p.m - row0 - warp * C::kRowsPerWarp + 3) >> 2;
-    jmax = jmax < 0 ? 0 : (jmax > R ? R : jmax);
-
     mbar_wait(sBar, parity0);
     parity0 ^= 1;
     build_tables<TM, NT>(sTab, sB, tid);
@@ -250,17 +244,16 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           // ---- lookups: acc[j] ^= T0[a byte 2*sub] ^ T1[a byte 2*sub+1] ----
           uint32_t const t0 = tcur + lane_off, t1 = tcur + kTableBytes + lane_off;
 #pragma unroll
+          // (rows past m read zero-filled A bits -> table row 0 = zeros; no branch needed)
           for (int j = 0; j < R; ++j) {
-            if (j < jmax) {
-              uint32_t const i0 = __byte_perm(aw[j], 0, 0x4440 + 2 * sub);
-              uint32_t const i1 = __byte_perm(aw[j], 0, 0x4441 + 2 * sub);
-              uint4 const v0 = lds128(t0 + i0 * kRowBytes);
-              uint4 const v1 = lds128(t1 + i1 * kRowBytes);
-              acc[j].x ^= v0.x ^ v1.x;
-              acc[j].y ^= v0.y ^ v1.y;
-              acc[j].z ^= v0.z ^ v1.z;
-              acc[j].w ^= v0.w ^ v1.w;
-            }
+            uint32_t const i0 = __byte_perm(aw[j], 0, 0x4440 + 2 * sub);
+            uint32_t const i1 = __byte_perm(aw[j], 0, 0x4441 + 2 * sub);
+            uint4 const v0 = lds128(t0 + i0 * kRowBytes);
+            uint4 const v1 = lds128(t1 + i1 * kRowBytes);
+            acc[j].x ^= v0.x ^ v1.x;
+            acc[j].y ^= v0.y ^ v1.y;
+            acc[j].z ^= v0.z ^ v1.z;
+            acc[j].w ^= v0.w ^ v1.w;
           }
           __syncthreads();
         }
@@ -363,10 +356,17 @@ int m4rm_num_sms() {
 
 void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) {
   if (A.nrows <= 0 || A.ncols <= 0 || B.ncols <= 0) return;   // empty product: C unchanged
+  static int variant = -1;
+  if (variant < 0) {
+    char const *env = getenv("M4RI_B200_VARIANT");   // tuning/debug only
+    variant = env ? atoi(env) : 0;
+  }
   if (A.nrows <= 256)
     launch_variant<256, 256>(C, A, B, stream);
-  else
+  else if (variant == 1)
     launch_variant<1024, 512>(C, A, B, stream);
+  else
+    launch_variant<1024, 256>(C, A, B, stream);
 }
 
 }  // namespace m4b
