@@ -83,6 +83,12 @@ void        m4ri_b200_release(void);                    /* free cached device wo
 char const *m4ri_b200_last_path(void);                  /* "m4rm" / "strassen:<levels>" of the last product */
 uint64_t    m4ri_b200_kernel_launches(void);            /* CUDA kernels launched by this library so far */
 
+/* Live timing of the M4RM leaf launches: between begin and end every leaf launch is bracketed
+ * by CUDA events on its stream.  end() (call after synchronising) returns the number of leaf
+ * launches, their summed device time in ms and their summed 2*m*l*n. */
+void     m4ri_b200_profile_begin(void);
+uint64_t m4ri_b200_profile_end(double *leaf_ms, double *leaf_bitops);
+
 /* Stand-alone host matrices (same layout/semantics as mzd_init / mzd_init_window /
  * mzd_free, m4ri/mzd.c:142-185) for programs that do not link libm4ri. */
 mzd_t *m4ri_b200_mzd_init(rci_t r, rci_t c);

@@ -73,6 +73,8 @@ def _declare(lib):
     lib.m4ri_b200_get_default_cutoff.restype = c_int
     lib.m4ri_b200_last_path.restype = c_char_p
     lib.m4ri_b200_kernel_launches.restype = c_uint64
+    lib.m4ri_b200_profile_end.argtypes = [POINTER(ctypes.c_double), POINTER(ctypes.c_double)]
+    lib.m4ri_b200_profile_end.restype = c_uint64
     lib.m4ri_b200_mzd_init.argtypes, lib.m4ri_b200_mzd_init.restype = [c_int, c_int], MzdP
     lib.m4ri_b200_mzd_init_window.argtypes = [MzdP, c_int, c_int, c_int, c_int]
     lib.m4ri_b200_mzd_init_window.restype = MzdP

@@ -295,6 +295,9 @@ void m4ri_b200_release(void) {
 char const *m4ri_b200_last_path(void) { return g.last_path; }
 uint64_t    m4ri_b200_kernel_launches(void) { return g_kernel_launches; }
 
+void m4ri_b200_profile_begin(void) { leaf_profile_begin(); }
+uint64_t m4ri_b200_profile_end(double *leaf_ms, double *leaf_bitops) { return leaf_profile_end(leaf_ms, leaf_bitops); }
+
 mzd_t *m4ri_b200_mzd_init(rci_t r, rci_t c) {
   mzd_t *M = static_cast<mzd_t *>(malloc(sizeof(mzd_t)));
   fill_header(M, r, c);

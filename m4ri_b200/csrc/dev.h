@@ -41,6 +41,8 @@ extern unsigned long long g_kernel_launches;  // counted by every launcher in th
 // C must already hold the addend (zeros for a plain product).
 void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream);
 int  m4rm_num_sms();
+void leaf_profile_begin();
+unsigned long long leaf_profile_end(double *ms, double *bitops);
 
 // ---- element-wise helpers on views (all 128-bit vectorised) --------------------------
 void launch_xor(DView C, DView A, DView B, cudaStream_t stream);        // C = A ^ B

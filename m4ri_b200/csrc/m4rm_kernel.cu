@@ -28,6 +28,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <utility>
+#include <vector>
+
 #include "dev.h"
 
 namespace m4b {
@@ -344,6 +347,38 @@ void launch_variant(DView Cv, DView A, DView B, cudaStream_t stream) {
 
 }  // namespace
 
+// ---- optional live timing of the leaf launches (bench.py's roofline figure) -----------------
+namespace {
+struct LeafProf {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+  size_t used = 0;
+  double bitops = 0;
+} g_prof;
+}  // namespace
+
+void leaf_profile_begin() {
+  g_prof.on = true;
+  g_prof.used = 0;
+  g_prof.bitops = 0;
+}
+
+// Returns the number of leaf launches since leaf_profile_begin(); *ms = summed device time of
+// those launches (CUDA events on the launching stream), *bitops = 2*m*l*n summed over them.
+// The caller must have synchronised the stream.
+unsigned long long leaf_profile_end(double *ms, double *bitops) {
+  double total = 0;
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    float t = 0;
+    M4B_CUDA(cudaEventElapsedTime(&t, g_prof.pool[i].first, g_prof.pool[i].second));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (bitops) *bitops = g_prof.bitops;
+  g_prof.on = false;
+  return g_prof.used;
+}
+
 int m4rm_num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -356,6 +391,18 @@ int m4rm_num_sms() {
 
 void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) {
   if (A.nrows <= 0 || A.ncols <= 0 || B.ncols <= 0) return;   // empty product: C unchanged
+  std::pair<cudaEvent_t, cudaEvent_t> *ev = nullptr;
+  if (g_prof.on) {
+    if (g_prof.used == g_prof.pool.size()) {
+      std::pair<cudaEvent_t, cudaEvent_t> e;
+      M4B_CUDA(cudaEventCreate(&e.first));
+      M4B_CUDA(cudaEventCreate(&e.second));
+      g_prof.pool.push_back(e);
+    }
+    ev = &g_prof.pool[g_prof.used++];
+    g_prof.bitops += 2.0 * A.nrows * (double)A.ncols * B.ncols;
+    M4B_CUDA(cudaEventRecord(ev->first, stream));
+  }
   static int variant = -1;
   if (variant < 0) {
     char const *env = getenv("M4RI_B200_VARIANT");   // tuning/debug only
@@ -367,6 +414,7 @@ void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) {
     launch_variant<1024, 512>(C, A, B, stream);
   else
     launch_variant<1024, 256>(C, A, B, stream);
+  if (ev) M4B_CUDA(cudaEventRecord(ev->second, stream));
 }
 
 }  // namespace m4b

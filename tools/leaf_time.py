@@ -9,7 +9,9 @@ import m4ri_b200  # noqa: E402
 
 lib = m4ri_b200.load_library()
 torch.cuda.init()
-stream = torch.cuda.current_stream().cuda_stream
+tstream = torch.cuda.Stream()          # a real (non-default) stream: handle 0 would mean "library stream"
+torch.cuda.set_stream(tstream)
+stream = tstream.cuda_stream
 
 
 def dev_random(rows, cols):
