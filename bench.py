@@ -222,8 +222,10 @@ def run_own_arm(args):
     if n % (128 * world):
         raise SystemExit("n must be a multiple of 128 * gpus")
     cutoff = args.cutoff
-    rows = n // world                      # this rank's row-block of A and C
-    brow = n // world                      # this rank's row-slice of B
+    from m4ri_b200 import shard
+    r0, r1 = shard.row_blocks(n, world)[rank]
+    rows = r1 - r0                         # this rank's row-block of A and C
+    brow = shard.padded_slice_rows(n, world)   # this rank's row-slice of B (n % (64*world) == 0: no padding)
     pitch = n // 64
 
     tstream = torch.cuda.Stream()
@@ -323,6 +325,20 @@ def run_own_arm(args):
     h2d = (rows + brow) * pitch * 8 * world
     d2h = rows * pitch * 8 * world
 
+    if args.verify:   # small-n correctness of this rank's block against the oracle (never at full size)
+        from tests import harness as H
+        step_e2e()
+        full_b = torch.empty((n, pitch), dtype=torch.int64)
+        full_b.copy_(tB)
+        Ao, Bo = H.new(rows, n), H.new(n, n)
+        H.storage(Ao)[:, :] = hA.numpy().view(np.uint64)
+        H.storage(Bo)[:, :] = full_b.numpy().view(np.uint64)
+        want = H.oracle().orc_mul(None, Ao, Bo, 0)
+        ok = bool(np.array_equal(H.storage(want), hC.numpy().view(np.uint64)))
+        print(f"[verify] rank {rank}: rows {r0}:{r1} {'OK' if ok else 'MISMATCH'}", file=sys.stderr, flush=True)
+        if not ok:
+            raise SystemExit(3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -402,6 +418,7 @@ def main():
     ap.add_argument("--n", type=int, default=65536)
     ap.add_argument("--cutoff", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="check this rank's C block against the oracle (small --n only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -88,7 +88,9 @@ mzd_t *alloc_result(rci_t r, rci_t c) {
   return ref_init ? ref_init(r, c) : m4ri_b200_mzd_init(r, c);
 }
 
-// ---- transfers --------------------------------------------------------------------------
+}  // namespace
+
+// ---- transfers (shared with multi.cu) ------------------------------------------------------
 void upload(DView dst, mzd_t const *src, cudaStream_t s) {
   if (src->nrows == 0 || src->ncols == 0) return;
   M4B_CUDA(cudaMemcpy2DAsync(dst.data, (size_t)dst.pitch * 8, src->data, (size_t)src->rowstride * 8,
@@ -119,6 +121,8 @@ void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp) {
 void zero_async(DView v, cudaStream_t s) {
   M4B_CUDA(cudaMemsetAsync(v.data, 0, (size_t)v.nrows * (size_t)v.pitch * 8, s));
 }
+
+namespace {
 
 int norm_cutoff(int cutoff, char const *who) {   // m4ri/strassen.c:349-354
   if (cutoff < 0) die("%s: cutoff must be >= 0.\n", who);
@@ -260,8 +264,25 @@ mzd_t *mzd_addmul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k) {
   return _mzd_mul_m4rm(C, A, B, k, 0);
 }
 
-mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) { return mzd_mul(C, A, B, cutoff); }
-mzd_t *mzd_addmul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) { return mzd_addmul(C, A, B, cutoff); }
+// Row-blocks of C over the GPUs chosen with m4ri_b200_set_num_devices (multi.cu); one GPU: same as mzd_mul.
+mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  if (ctx().num_devices <= 1) return mzd_mul(C, A, B, cutoff);
+  if (A->ncols != B->nrows) die("mzd_mul_mp: A ncols (%d) need to match B nrows (%d).\n", A->ncols, B->nrows);
+  cutoff = norm_cutoff(cutoff, "mzd_mul_mp");
+  C = checked("mzd_mul_mp", C, A, B);
+  multi_product(C, A, B, cutoff, true, ctx().num_devices, ctx().last_path, sizeof ctx().last_path);
+  return C;
+}
+
+mzd_t *mzd_addmul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  if (ctx().num_devices <= 1) return mzd_addmul(C, A, B, cutoff);
+  if (A->ncols != B->nrows) die("mzd_addmul_mp: A ncols (%d) need to match B nrows (%d).\n", A->ncols, B->nrows);
+  cutoff = norm_cutoff(cutoff, "mzd_addmul_mp");
+  C = checked("mzd_addmul_mp", C, A, B);
+  if (A->nrows == 0 || A->ncols == 0 || B->ncols == 0) return C;
+  multi_product(C, A, B, cutoff, false, ctx().num_devices, ctx().last_path, sizeof ctx().last_path);
+  return C;
+}
 
 // ---- Part 2: extension API ------------------------------------------------------------------
 
@@ -287,6 +308,7 @@ void m4ri_b200_set_default_cutoff(int cutoff) { g.default_cutoff = cutoff > 0 ? 
 int  m4ri_b200_get_default_cutoff(void) { return g.default_cutoff ? g.default_cutoff : kBuiltinCutoff; }
 
 void m4ri_b200_release(void) {
+  multi_release();
   if (!g.ready) return;
   cudaStreamSynchronize(g.stream);
   g.ws.destroy();

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "../../include/m4ri_b200.h"
 
 namespace m4b {
@@ -49,6 +51,16 @@ void launch_xor(DView C, DView A, DView B, cudaStream_t stream);        // C = A
 void launch_zero(DView C, cudaStream_t stream);                          // C = 0
 void launch_copy(DView C, DView A, cudaStream_t stream);                 // C = A
 void launch_mask_excess(DView C, cudaStream_t stream);                   // clear bits >= ncols of last word(s)
+
+// ---- host <-> device transfers (capi.cu) ----------------------------------------------
+void upload(DView dst, mzd_t const *src, cudaStream_t s);                 // excess bits cleared on device
+void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp);   // only valid bits of dst change
+void zero_async(DView v, cudaStream_t s);
+
+// ---- multi-GPU row-block product (multi.cu) --------------------------------------------
+void multi_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool clear, int num_devices,
+                   char *path_out, size_t path_len);
+void multi_release();
 
 // ---- host scheduler ------------------------------------------------------------------
 struct Workspace;  // bump allocator over one cached device slab

@@ -321,11 +321,13 @@ CUtensorMap make_map(DView V, int box_w32, int box_rows) {
 template <int TM, int NT>
 void launch_variant(DView Cv, DView A, DView B, cudaStream_t stream) {
   using C = Cfg<TM, NT>;
-  static bool configured = false;
+  static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
   auto kern = m4rm_streamk_kernel<TM, NT>;
-  if (!configured) {
+  int dev = 0;
+  M4B_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
     M4B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured = true;
+    configured[dev & 63] = true;
   }
   Params p;
   p.C = reinterpret_cast<unsigned long long *>(Cv.data);

@@ -1,0 +1,91 @@
+"""CPU test (-m "not gpu") of the N>1 path's host logic: world_size 2 and 3 over gloo.
+
+Each rank holds a row-block of A and a padded row-slice of B, all-gathers B with
+torch.distributed (gloo here, NCCL on the GPU box — same call in bench.py), multiplies locally
+(the ORACLE stands in for the GPU leaf: this test is about the partition and the exchange), and
+rank 0 checks the stacked row-blocks against the oracle's product of the full matrices."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from m4ri_b200 import shard
+from tests import harness as H
+
+
+def test_row_blocks_cover_and_align():
+    for nrows, world in [(65536, 8), (1000, 3), (64, 8), (1, 2), (129, 2), (4100, 4)]:
+        blocks = shard.row_blocks(nrows, world)
+        assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == nrows
+        for (a0, a1), (b0, b1) in zip(blocks, blocks[1:]):
+            assert a1 == b0 and a0 <= a1
+        assert all(r0 % 64 == 0 for r0, _ in blocks if r0 < nrows)
+        assert shard.padded_slice_rows(nrows, world) * world >= nrows
+
+
+def _matrix_from(words_2d, ncols):
+    M = H.new(words_2d.shape[0], ncols)
+    H.storage(M)[:, : words_2d.shape[1]] = words_2d
+    return M
+
+
+def _worker(rank, world, port, m, l, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(42)                       # every rank derives the same full inputs
+    wl, wn = (l + 63) // 64, (n + 63) // 64
+    A = rng.integers(0, 2**64, size=(m, wl), dtype=np.uint64)
+    B = rng.integers(0, 2**64, size=(l, wn), dtype=np.uint64)
+    if l % 64:
+        A[:, -1] &= np.uint64((1 << (l % 64)) - 1)
+    if n % 64:
+        B[:, -1] &= np.uint64((1 << (n % 64)) - 1)
+    r0, r1 = shard.row_blocks(m, world)[rank]
+    per = shard.padded_slice_rows(l, world)
+    s0, s1 = min(l, rank * per), min(l, (rank + 1) * per)
+    b_slice = np.zeros((per, wn), dtype=np.uint64)
+    b_slice[: s1 - s0] = B[s0:s1]
+
+    def all_gather(sl):
+        out = torch.empty((world * per, wn), dtype=torch.int64)
+        dist.all_gather_into_tensor(out.view(-1), torch.from_numpy(sl.view(np.int64)).reshape(-1))
+        return out.numpy().view(np.uint64)
+
+    def local_mul(a_blk, b_full):
+        if a_blk.shape[0] == 0:
+            return np.zeros((0, wn), dtype=np.uint64)
+        Am, Bm = _matrix_from(a_blk, l), _matrix_from(b_full[:l], n)
+        Cm = H.oracle().orc_mul(None, Am, Bm, 0)
+        out = H.storage(Cm)[:, :wn].copy()
+        H.free(Am, Bm, Cm)
+        return out
+
+    c_blk = shard.sharded_product(rank, world, A[r0:r1], b_slice, all_gather, local_mul)
+    gathered = [None] * world
+    dist.gather_object((r0, r1, c_blk), gathered if rank == 0 else None, dst=0)
+    if rank == 0:
+        C = np.zeros((m, wn), dtype=np.uint64)
+        for g0, g1, blk in gathered:
+            C[g0:g1] = blk
+        Am, Bm = _matrix_from(A, l), _matrix_from(B, n)
+        want = H.oracle().orc_mul(None, Am, Bm, 0)
+        q.put(bool(np.array_equal(C, H.storage(want)[:, :wn])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (300, 200, 260)), (2, (130, 1000, 70)), (3, (200, 333, 129))])
+def test_sharded_product_over_gloo(world, shape):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + world * 7 + shape[0]) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, *shape, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
