@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — GF(2) matmul bit-ops/s (2*n^3) at n = 65536 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 65536] [--cutoff 0]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 65536] [--cutoff 0]
 
 Own arm ("ours"):  one step = one mzd_mul of two random n x n GF(2) matrices (Strassen-Winograd
 over the M4RM leaf kernel, all on the GPU).
@@ -415,7 +415,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--size", dest="n", type=int, default=65536, help="n of the n x n x n product")
     ap.add_argument("--cutoff", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="check this rank's C block against the oracle (small --n only)")

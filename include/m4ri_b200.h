@@ -123,6 +123,8 @@ void m4ri_b200_sync(void *stream);
  * clear != 0 computes C = A*B, clear == 0 computes C ^= A*B. */
 void m4ri_b200_dmul_m4rm(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int clear, void *stream);
 void m4ri_b200_dmul(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int cutoff, int clear, void *stream);
+/* as dmul with the Strassen depth given explicitly (0 = leaf only); for cutoff sweeps. */
+void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int levels, int clear, void *stream);
 /* C = A ^ B on device matrices (the device form of _mzd_add, m4ri/mzd.c:1471-1583). */
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream);
 

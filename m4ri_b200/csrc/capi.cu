@@ -411,6 +411,13 @@ void m4ri_b200_dmul(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat c
   device_product(C, A, B, levels, clear != 0, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
 }
 
+void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int levels, int clear,
+                           void *stream) {
+  if (levels < 0 || levels > 12) die("m4ri_b200_dmul_levels: levels must be in 0..12\n");
+  while (levels > 0 && ((A->nrows >> levels) < 1 || (A->ncols >> levels) < 128 || (B->ncols >> levels) < 128)) --levels;
+  device_product(C, A, B, levels, clear != 0, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+}
+
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {
   if (A->nrows != B->nrows || A->ncols != B->ncols || C->nrows != A->nrows || C->ncols != A->ncols)
     die("m4ri_b200_dadd: dimension mismatch\n");

@@ -9,22 +9,32 @@
 //   * The caller pads the operands with zeros to multiples of 2^levels rows and 128*2^levels
 //     columns (capi.cu), so every level halves exactly on 128-bit boundaries and there are no
 //     edge strips (strassen.c:171-204) and no window copies (strassen.c:54-62).
-//   * The recursion depth is fixed up front by strassen_levels(), which applies the
-//     reference's own leaf test `3*dim < 4*cutoff` (strassen.c:39,51) level by level.
+//   * The recursion depth is fixed up front by strassen_levels(): the reference's leaf test
+//     (strassen.c:39,51) restated by volume so that rectangular row-blocks still recurse.
 //   * Temporaries come from a bump allocator over one cached device slab (no malloc per node).
 #include "dev.h"
 #include "workspace.h"
 
 namespace m4b {
 
-static inline bool closer(int a, int cutoff) { return 3LL * a < 4LL * cutoff; }
+// Leaf test.  The reference stops when ANY dimension is "closer to cutoff than its half"
+// (3*dim < 4*cutoff, strassen.c:39,51), i.e. its leaves keep every dimension >= 2/3*cutoff.  For
+// square problems we reproduce exactly that depth.  A rectangular problem (the row-block a GPU owns in
+// the multi-GPU split is m/G x l x n) would never recurse under that rule although each half-product
+// is still big enough to run the persistent leaf at full efficiency, so the device rule is by VOLUME:
+// split while the half-problem keeps at least (2/3*cutoff)^3 bit-triples and every dimension of it
+// stays >= kMinLeafDim.  Depth never changes a result bit.
+static constexpr int kMinLeafDim = 2048;
 
 int strassen_levels(int m, int k, int n, int cutoff) {
+  double const min_volume = (2.0 / 3.0 * cutoff) * (2.0 / 3.0 * cutoff) * (2.0 / 3.0 * cutoff);
+  int const min_dim = cutoff < kMinLeafDim ? (cutoff * 2 / 3 > 64 ? cutoff * 2 / 3 : 64) : kMinLeafDim;
   int levels = 0;
-  while (!(closer(m, cutoff) || closer(k, cutoff) || closer(n, cutoff)) && m >= 2 && k >= 256 && n >= 256) {
-    m = (m + 1) / 2;
-    k = (k + 1) / 2;
-    n = (n + 1) / 2;
+  while (true) {
+    int const m2 = (m + 1) / 2, k2 = (k + 1) / 2, n2 = (n + 1) / 2;
+    if (m2 < min_dim || k2 < (min_dim < 128 ? 128 : min_dim) || n2 < (min_dim < 128 ? 128 : min_dim)) break;
+    if ((double)m2 * k2 * n2 < min_volume) break;
+    m = m2; k = k2; n = n2;
     ++levels;
   }
   return levels;

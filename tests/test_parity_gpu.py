@@ -301,3 +301,20 @@ def test_full_size_freivalds_and_linearity(lib, shape, cutoff, fn):
     getattr(lib, fn)(D, A2, B, cutoff)
     assert np.array_equal(H.storage(C), H.storage(D))
     H.free(A, B, C, A2, D)
+
+
+def test_c_program_linked_against_both_libraries(tmp_path):
+    """a C program in the style of tests/test_multiplication.c, linked with
+    libm4ri_b200.so first and the unmodified reference second."""
+    if not os.path.exists(H.REF_SO):
+        pytest.skip("oracle/_ref/libm4ri_ref.so not present")
+    exe = tmp_path / "dropin"
+    libdir = os.path.dirname(m4ri_b200.LIB_PATH)
+    refdir = os.path.dirname(H.REF_SO)
+    subprocess.check_call(["gcc", "-O1", "-std=gnu99", "-D_DEFAULT_SOURCE", "-I", os.path.join(H.ROOT, "include"),
+                           os.path.join(H.ROOT, "tests", "c", "dropin.c"), "-o", str(exe),
+                           "-L", libdir, "-lm4ri_b200", "-L", refdir, "-l:libm4ri_ref.so", "-lm",
+                           f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{refdir}"])
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "All tests passed." in p.stdout

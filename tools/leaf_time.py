@@ -31,6 +31,8 @@ def run(m, l, n, cutoff, iters=5):
     def go():
         if cutoff < 0:
             lib.m4ri_b200_dmul_m4rm(dC, dA, dB, 1, stream)
+        elif cutoff < 16:          # small values mean "this many Strassen levels"
+            lib.m4ri_b200_dmul_levels(dC, dA, dB, cutoff, 1, stream)
         else:
             lib.m4ri_b200_dmul(dC, dA, dB, cutoff, 1, stream)
 
