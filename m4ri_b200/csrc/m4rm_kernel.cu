@@ -98,6 +98,9 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_xor64(unsigned long long *p, uint32_t lo, uint32_t hi) {
   unsigned long long v = (static_cast<unsigned long long>(hi) << 32) | lo;
   asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -124,7 +127,7 @@ struct Cfg {
   static constexpr int kSmemBytes  = kOffBar + 64;
   static constexpr uint32_t kSlabTxBytes = kASlabBytes + kBSlabBytes;
   static_assert(kGrayBits > 0, "unsupported thread count");
-  static_assert(R >= 1 && kRowsPerWarp % 4 == 0, "bad tile shape");
+  static_assert(R >= 2 && kRowsPerWarp % 8 == 0, "bad tile shape");
 };
 
 // Build the two 256-entry tables of one step from 16 rows of the B slab.
@@ -159,7 +162,49 @@ __device__ __forceinline__ void build_tables(uint32_t tbuf, uint32_t brows16, in
   }
 }
 
+// Same tables, warp-per-entry mapping: the 32 lanes of a warp own the 32 words of one table row
+// (LDS.32 / STS.32 = exactly one 128-byte wavefront each), a warp walks 512/warps entries in Gray
+// order.  Versus the 8-lane mapping this removes the 4-pass cost of LDS.128 for the B rows (every
+// quarter-warp re-read the same 128 bytes): 8 wavefronts of B loads per warp and step instead of 32.
 template <int TM, int NT>
+__device__ __forceinline__ void build_tables_w32(uint32_t tbuf, uint32_t brows16, int tid) {
+  constexpr int W  = NT / 32;
+  constexpr int E  = 512 / W;                                   // entries per warp and step
+  constexpr int GB = E == 64 ? 6 : (E == 32 ? 5 : (E == 16 ? 4 : -1));
+  static_assert(GB > 0, "unsupported warp count");
+  int const warp = tid >> 5, lane = tid & 31;
+  int const t = warp / (W / 2), h = warp % (W / 2);             // table, index bits GB..7
+  uint32_t const src = brows16 + (t * 8) * kRowBytes + lane * 4;
+  uint32_t low[GB];
+#pragma unroll
+  for (int b = 0; b < GB; ++b) low[b] = lds32(src + b * kRowBytes);
+  uint32_t e = 0;
+#pragma unroll
+  for (int b = GB; b < 8; ++b) e ^= lds32(src + b * kRowBytes) & (0u - ((h >> (b - GB)) & 1u));
+  uint32_t const dst = tbuf + t * kTableBytes + (h << GB) * kRowBytes + lane * 4;
+  sts32(dst, e);
+#pragma unroll
+  for (int i = 1; i < E; ++i) {
+    e ^= low[(i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : (i & 8) ? 3 : (i & 16) ? 4 : 5];
+    sts32(dst + (i ^ (i >> 1)) * kRowBytes, e);
+  }
+}
+
+template <int TM, int NT, int BW>
+__device__ __forceinline__ void build_step(uint32_t tbuf, uint32_t brows16, int tid) {
+  if (BW == 4) build_tables_w32<TM, NT>(tbuf, brows16, tid);
+  else         build_tables<TM, NT>(tbuf, brows16, tid);
+}
+
+// MAP selects the lane -> C-element mapping of the lookup loop:
+//   0: 8 lanes x 16 B own one C row (1024 bits); a warp LDS.128 serves 4 rows.
+//   1: 4 lanes x 16 B own one HALF row; lanes 0-3 of a quarter-warp take one row, lanes 4-7 the next,
+//      and the two halves are fetched by two LDS.128 with the halves swapped between the lane groups, so
+//      every quarter-warp pass still reads 128 contiguous-bank bytes (low half of one table row + high
+//      half of another: conflict-free).  A warp instruction serves 8 rows, so a thread holds half as
+//      many rows (R/2) of twice the width: half the A-index registers, half the A-word loads and index
+//      extractions for the same number of table lookups.
+template <int TM, int NT, int BW, int MAP>
 __global__ void __launch_bounds__(NT, 1)
 m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p) {
   using C = Cfg<TM, NT>;
@@ -173,6 +218,9 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
   int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int const q = lane >> 3, c = lane & 7;
+  int const hi = (lane >> 2) & 1, c4 = lane & 3;          // MAP 1: row parity within the quarter, 16 B chunk of a half row
+  constexpr int RT = MAP == 1 ? R / 2 : R;                 // rows per thread
+  constexpr int AW = MAP == 1 ? 2 : 1;                     // uint4 accumulators per row
 
   if (tid == 0) {
     mbar_init(sBar, 1);
@@ -186,8 +234,11 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   long long const u_end   = p.total_units * (long long)(blockIdx.x + 1) / gridDim.x;
   uint32_t parity0 = 0, parity1 = 0;             // phase of each ring slot
 
-  uint32_t const a_row_off = (warp * C::kRowsPerWarp + q) * 16;   // first A row of this lane group
-  uint32_t const lane_off  = c * 16;
+  uint32_t const a_row_off = MAP == 1 ? (warp * C::kRowsPerWarp + q * 2 + hi) * 16   // first A row of this lane group
+                                      : (warp * C::kRowsPerWarp + q) * 16;
+  uint32_t const a_row_step = MAP == 1 ? 128 : 64;         // 8 (4) rows further per j
+  uint32_t const lane_off  = MAP == 1 ? hi * 64 + c4 * 16 : c * 16;
+  uint32_t const lane_off2 = (hi ^ 1) * 64 + c4 * 16;      // MAP 1: the other half of the row
 
   for (long long u = u_begin; u < u_end;) {
     int const tile  = (int)(u / p.slabs);
@@ -213,13 +264,15 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (nseg > 1) issue(1);
     }
 
-    uint4 acc[R];
+    uint4 acc[RT][AW];
 #pragma unroll
-    for (int j = 0; j < R; ++j) acc[j] = make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < RT; ++j)
+#pragma unroll
+      for (int h = 0; h < AW; ++h) acc[j][h] = make_uint4(0, 0, 0, 0);
 
     mbar_wait(sBar, parity0);
     parity0 ^= 1;
-    build_tables<TM, NT>(sTab, sB, tid);
+    build_step<TM, NT, BW>(sTab, sB, tid);
     __syncthreads();
 
     for (int i = 0; i < nseg; ++i) {
@@ -228,9 +281,9 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       uint32_t const bS = sB + slot * kBSlabBytes;
 #pragma unroll 1
       for (int pr = 0; pr < kStepsPerSlab / 2; ++pr) {
-        uint32_t aw[R];
+        uint32_t aw[RT];
 #pragma unroll
-        for (int j = 0; j < R; ++j) aw[j] = lds32(aS + j * 64 + pr * 4);
+        for (int j = 0; j < RT; ++j) aw[j] = lds32(aS + j * a_row_step + pr * 4);
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           int const step = pr * 2 + sub;
@@ -238,25 +291,34 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           uint32_t const tnext = sTab + (sub ^ 1) * kStepBufBytes;
           // ---- build tables for the next step into the other buffer ----
           if (step < kStepsPerSlab - 1) {
-            build_tables<TM, NT>(tnext, bS + (step + 1) * 16 * kRowBytes, tid);
+            build_step<TM, NT, BW>(tnext, bS + (step + 1) * 16 * kRowBytes, tid);
           } else if (i + 1 < nseg) {
             if (slot == 0) { mbar_wait(sBar + 8, parity1); parity1 ^= 1; }
             else           { mbar_wait(sBar, parity0);     parity0 ^= 1; }
-            build_tables<TM, NT>(tnext, sB + (slot ^ 1) * kBSlabBytes, tid);
+            build_step<TM, NT, BW>(tnext, sB + (slot ^ 1) * kBSlabBytes, tid);
           }
           // ---- lookups: acc[j] ^= T0[a byte 2*sub] ^ T1[a byte 2*sub+1] ----
-          uint32_t const t0 = tcur + lane_off, t1 = tcur + kTableBytes + lane_off;
-#pragma unroll
           // (rows past m read zero-filled A bits -> table row 0 = zeros; no branch needed)
-          for (int j = 0; j < R; ++j) {
+          uint32_t const t0 = tcur + lane_off, t1 = tcur + kTableBytes + lane_off;
+          uint32_t const u0 = tcur + lane_off2, u1 = tcur + kTableBytes + lane_off2;
+#pragma unroll
+          for (int j = 0; j < RT; ++j) {
             uint32_t const i0 = __byte_perm(aw[j], 0, 0x4440 + 2 * sub);
             uint32_t const i1 = __byte_perm(aw[j], 0, 0x4441 + 2 * sub);
             uint4 const v0 = lds128(t0 + i0 * kRowBytes);
             uint4 const v1 = lds128(t1 + i1 * kRowBytes);
-            acc[j].x ^= v0.x ^ v1.x;
-            acc[j].y ^= v0.y ^ v1.y;
-            acc[j].z ^= v0.z ^ v1.z;
-            acc[j].w ^= v0.w ^ v1.w;
+            acc[j][0].x ^= v0.x ^ v1.x;
+            acc[j][0].y ^= v0.y ^ v1.y;
+            acc[j][0].z ^= v0.z ^ v1.z;
+            acc[j][0].w ^= v0.w ^ v1.w;
+            if (MAP == 1) {
+              uint4 const w0 = lds128(u0 + i0 * kRowBytes);
+              uint4 const w1 = lds128(u1 + i1 * kRowBytes);
+              acc[j][AW - 1].x ^= w0.x ^ w1.x;
+              acc[j][AW - 1].y ^= w0.y ^ w1.y;
+              acc[j][AW - 1].z ^= w0.z ^ w1.z;
+              acc[j][AW - 1].w ^= w0.w ^ w1.w;
+            }
           }
           __syncthreads();
         }
@@ -267,15 +329,18 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
     // ---- merge the partial tile into C (exact: XOR is associative and commutative) ----
     {
-      int const wcol = tn * (kTileBits / 64) + c * 2;
-      int const rbase = row0 + warp * C::kRowsPerWarp + q;
+      int const rbase = row0 + warp * C::kRowsPerWarp + (MAP == 1 ? q * 2 + hi : q);
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        int const row = rbase + 4 * j;
+      for (int j = 0; j < RT; ++j) {
+        int const row = rbase + (MAP == 1 ? 8 : 4) * j;
         if (row < p.m) {
-          unsigned long long *dst = p.C + (long long)row * p.pitchC + wcol;
-          if (wcol < p.nwordsC) red_xor64(dst, acc[j].x, acc[j].y);
-          if (wcol + 1 < p.nwordsC) red_xor64(dst + 1, acc[j].z, acc[j].w);
+#pragma unroll
+          for (int h = 0; h < AW; ++h) {
+            int const wcol = tn * (kTileBits / 64) + (MAP == 1 ? (hi ^ h) * 8 + c4 * 2 : c * 2);
+            unsigned long long *dst = p.C + (long long)row * p.pitchC + wcol;
+            if (wcol < p.nwordsC) red_xor64(dst, acc[j][h].x, acc[j][h].y);
+            if (wcol + 1 < p.nwordsC) red_xor64(dst + 1, acc[j][h].z, acc[j][h].w);
+          }
         }
       }
     }
@@ -318,11 +383,11 @@ CUtensorMap make_map(DView V, int box_w32, int box_rows) {
   return map;
 }
 
-template <int TM, int NT>
+template <int TM, int NT, int BW, int MAP>
 void launch_variant(DView Cv, DView A, DView B, cudaStream_t stream) {
   using C = Cfg<TM, NT>;
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
-  auto kern = m4rm_streamk_kernel<TM, NT>;
+  auto kern = m4rm_streamk_kernel<TM, NT, BW, MAP>;
   int dev = 0;
   M4B_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
@@ -411,11 +476,15 @@ void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) {
     variant = env ? atoi(env) : 0;
   }
   if (A.nrows <= 256)
-    launch_variant<256, 256>(C, A, B, stream);
+    launch_variant<256, 256, 4, 1>(C, A, B, stream);
   else if (variant == 1)
-    launch_variant<1024, 512>(C, A, B, stream);
+    launch_variant<1024, 256, 4, 0>(C, A, B, stream);
+  else if (variant == 2)
+    launch_variant<1024, 256, 16, 0>(C, A, B, stream);
+  else if (variant == 3)
+    launch_variant<1024, 256, 16, 1>(C, A, B, stream);
   else
-    launch_variant<1024, 256>(C, A, B, stream);
+    launch_variant<1024, 256, 4, 1>(C, A, B, stream);
   if (ev) M4B_CUDA(cudaEventRecord(ev->second, stream));
 }
 
