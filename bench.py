@@ -233,9 +233,10 @@ def run_own_arm(args):
     sh = ctypes.c_void_p(tstream.cuda_stream)
 
     # ---- host inputs (pinned): A row-block, B row-slice, C row-block -------------------------
-    hA = torch.empty((rows, pitch), dtype=torch.int64, pin_memory=True)
-    hB = torch.empty((brow, pitch), dtype=torch.int64, pin_memory=True)
-    hC = torch.zeros((rows, pitch), dtype=torch.int64, pin_memory=True)
+    pin = not args.pageable
+    hA = torch.empty((rows, pitch), dtype=torch.int64, pin_memory=pin)
+    hB = torch.empty((brow, pitch), dtype=torch.int64, pin_memory=pin)
+    hC = torch.zeros((rows, pitch), dtype=torch.int64, pin_memory=pin)
     fill_random_words(hA.numpy().view(np.uint64), 1000 + rank)
     fill_random_words(hB.numpy().view(np.uint64), 2000 + rank)
     mA = make_header(MzdT, hA.data_ptr(), rows, n, pitch)
@@ -398,7 +399,8 @@ def run_own_arm(args):
                    "path": path, "parallelism": f"row-block x{world}" + (", NCCL all-gather of B per step" if world > 1 else ""),
                    "l2": "inputs (3 x %d MiB) exceed the 126 MB L2; no flush needed" % (n * n // 8 >> 20)},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "api": "mzd_mul(C, A, B, cutoff) on pinned host mzd_t" if world == 1 else
+                "d2h_bytes_per_step": d2h, "host_memory": "pageable" if args.pageable else "pinned",
+                "api": "mzd_mul(C, A, B, cutoff) on host mzd_t" if world == 1 else
                 "upload + all_gather + m4ri_b200_dmul + download per rank"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
     }
@@ -418,6 +420,7 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=65536, help="n of the n x n x n product")
     ap.add_argument("--cutoff", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pageable", action="store_true", help="e2e with pageable (malloc) host matrices instead of pinned")
     ap.add_argument("--verify", action="store_true", help="check this rank's C block against the oracle (small --n only)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -41,6 +41,7 @@ struct Ctx {
   int          num_devices = 1;
   int          default_cutoff = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // PCIe transfers of the host path, overlapped with `stream`
   Workspace    ws;
   std::vector<word> host_tmp;
   char         last_path[64] = "none";
@@ -56,6 +57,7 @@ Ctx &ctx() {
     if (g.device >= 0) M4B_CUDA(cudaSetDevice(g.device));
     M4B_CUDA(cudaGetDevice(&g.device));
     M4B_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    M4B_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     if (!g.default_cutoff) {
       char const *env = getenv("M4RI_B200_CUTOFF");
       g.default_cutoff = env && atoi(env) > 0 ? atoi(env) : kBuiltinCutoff;
@@ -99,7 +101,10 @@ void upload(DView dst, mzd_t const *src, cudaStream_t s) {
 }
 
 // Device rows -> host matrix, touching only bits (i < nrows, j < ncols) of the host matrix.
-void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp) {
+// Whole words go straight into the host rows; a partial last word is staged in `tmp` and merged under
+// high_bitmask by download_finish() once the stream has been synchronised.
+void download_async(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp) {
+  tmp.clear();
   if (dst->nrows == 0 || dst->ncols == 0) return;
   int64_t const full = dst->ncols / 64;   // whole words per row
   if (full)
@@ -109,12 +114,24 @@ void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp) {
     tmp.resize((size_t)dst->nrows);
     M4B_CUDA(cudaMemcpy2DAsync(tmp.data(), 8, src.data + full, (size_t)src.pitch * 8, 8, (size_t)dst->nrows,
                                cudaMemcpyDeviceToHost, s));
+  }
+}
+
+void download_finish(mzd_t *dst, std::vector<word> const &tmp) {
+  if (tmp.empty()) return;
+  int64_t const full = dst->ncols / 64;
+  word const mask = dst->high_bitmask;
+  for (rci_t i = 0; i < dst->nrows; ++i) {
+    word *w = dst->data + (int64_t)i * dst->rowstride + full;
+    *w = (*w & ~mask) | (tmp[(size_t)i] & mask);
+  }
+}
+
+void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp) {
+  download_async(dst, src, s, tmp);
+  if (!tmp.empty()) {
     M4B_CUDA(cudaStreamSynchronize(s));
-    word const mask = dst->high_bitmask;
-    for (rci_t i = 0; i < dst->nrows; ++i) {
-      word *w = dst->data + (int64_t)i * dst->rowstride + full;
-      *w = (*w & ~mask) | (tmp[(size_t)i] & mask);
-    }
+    download_finish(dst, tmp);
   }
 }
 
@@ -130,6 +147,89 @@ int norm_cutoff(int cutoff, char const *who) {   // m4ri/strassen.c:349-354
   cutoff = cutoff / 64 * 64;
   return cutoff < 64 ? 64 : cutoff;
 }
+
+// A clipped window of a host matrix (header only; shares the words).  c0 must be a multiple of 64.
+mzd_t host_window(mzd_t const *M, int r0, int c0, int r1, int c1) {
+  mzd_t W = *M;
+  r1 = r1 < M->nrows ? r1 : M->nrows;
+  c1 = c1 < M->ncols ? c1 : M->ncols;
+  W.nrows = r1 > r0 ? r1 - r0 : 0;
+  W.ncols = c1 > c0 ? c1 - c0 : 0;
+  W.width = (W.ncols + 63) / 64;
+  W.high_bitmask = left_mask(W.ncols % 64);
+  W.flags = kFlagWindow | (W.ncols % 64 ? kFlagExcess : 0);
+  W.data = M->data + (int64_t)r0 * M->rowstride + c0 / 64;
+  return W;
+}
+
+// Overlap of PCIe transfers with the top level of the Strassen schedule (strassen.cu: TopHooks):
+// operand quadrants are uploaded on the copy stream in the order the schedule first reads them and the
+// compute stream waits on per-quadrant events; result quadrants are downloaded as soon as they are
+// final (three of the four are final before the last of the seven products starts).
+struct HostOverlap : TopHooks {
+  Ctx &c;
+  mzd_t *C;
+  mzd_t const *A, *B;
+  DView dA, dB, dC;
+  bool upA[4] = {}, upB[4] = {}, upC[4] = {};
+  std::vector<cudaEvent_t> events;
+  std::vector<word> tails[4];
+  mzd_t cwin[4];
+
+  HostOverlap(Ctx &c_, mzd_t *C_, mzd_t const *A_, mzd_t const *B_, DView a, DView b, DView cc)
+      : c(c_), C(C_), A(A_), B(B_), dA(a), dB(b), dC(cc) {}
+  ~HostOverlap() override {
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+  }
+  cudaEvent_t event() {
+    cudaEvent_t e;
+    M4B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    events.push_back(e);
+    return e;
+  }
+  static void quad(DView const &V, int q, int &r0, int &c0, int &r1, int &c1) {
+    int const rh = V.nrows / 2, ch = V.ncols / 2;
+    r0 = (q & 2) ? rh : 0;  r1 = r0 + rh;
+    c0 = (q & 1) ? ch : 0;  c1 = c0 + ch;
+  }
+  void up(mzd_t const *M, DView const &V, int q, bool *done) {
+    if (done[q]) return;
+    done[q] = true;
+    int r0, c0, r1, c1;
+    quad(V, q, r0, c0, r1, c1);
+    mzd_t W = host_window(M, r0, c0, r1, c1);
+    if (W.nrows > 0 && W.ncols > 0) upload(V.sub(r0, c0, r0 + W.nrows, c0 + W.ncols), &W, c.copy_stream);
+    cudaEvent_t e = event();
+    M4B_CUDA(cudaEventRecord(e, c.copy_stream));
+    M4B_CUDA(cudaStreamWaitEvent(c.stream, e, 0));
+  }
+  void need_a(int q) override { up(A, dA, q, upA); }
+  void need_b(int q) override { up(B, dB, q, upB); }
+  void need_c(int q) override { up(C, dC, q, upC); }
+  // D2H calls are only ISSUED in finish(), after every kernel has been enqueued: a copy into pageable
+  // host memory blocks the calling thread, and blocking here would stall the rest of the schedule.
+  cudaEvent_t ready[4] = {};
+  int order[4], ndone = 0;
+  void done_c(int q) override {
+    ready[q] = event();
+    M4B_CUDA(cudaEventRecord(ready[q], c.stream));
+    order[ndone++] = q;
+  }
+  void finish() {
+    for (int i = 0; i < ndone; ++i) {
+      int const q = order[i];
+      int r0, c0, r1, c1;
+      quad(dC, q, r0, c0, r1, c1);
+      cwin[q] = host_window(C, r0, c0, r1, c1);
+      M4B_CUDA(cudaStreamWaitEvent(c.copy_stream, ready[q], 0));
+      if (cwin[q].nrows > 0 && cwin[q].ncols > 0)
+        download_async(&cwin[q], dC.sub(r0, c0, r0 + cwin[q].nrows, c0 + cwin[q].ncols), c.copy_stream, tails[q]);
+    }
+    M4B_CUDA(cudaStreamSynchronize(c.copy_stream));
+    M4B_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < ndone; ++i) download_finish(&cwin[order[i]], tails[order[i]]);
+  }
+};
 
 // The one host->device->host product path behind every reference-named entry point.
 void host_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool clear, bool strassen) {
@@ -147,15 +247,25 @@ void host_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool cle
   DView dA = c.ws.alloc(mp, lp), dB = c.ws.alloc(lp, np), dC = c.ws.alloc(mp, np);
   zero_async(dA, s);
   zero_async(dB, s);
-  upload(dA, A, s);
-  upload(dB, B, s);
-  if (!clear) {
-    zero_async(dC, s);
-    upload(dC, C, s);
+  if (!clear) zero_async(dC, s);
+  if (levels > 0 && l > 0) {
+    // transfers ride the copy stream, ordered after the zero fills
+    cudaEvent_t zeroed;
+    M4B_CUDA(cudaEventCreateWithFlags(&zeroed, cudaEventDisableTiming));
+    M4B_CUDA(cudaEventRecord(zeroed, s));
+    M4B_CUDA(cudaStreamWaitEvent(c.copy_stream, zeroed, 0));
+    HostOverlap ov(c, C, A, B, dA, dB, dC);
+    strassen_mul(dC, dA, dB, levels, clear, c.ws, s, &ov);
+    ov.finish();
+    M4B_CUDA(cudaEventDestroy(zeroed));
+  } else {
+    upload(dA, A, s);
+    upload(dB, B, s);
+    if (!clear) upload(dC, C, s);
+    strassen_mul(dC, dA, dB, levels, clear, c.ws, s);
+    download(C, dC, s, c.host_tmp);
+    M4B_CUDA(cudaStreamSynchronize(s));
   }
-  strassen_mul(dC, dA, dB, levels, clear, c.ws, s);
-  download(C, dC, s, c.host_tmp);
-  M4B_CUDA(cudaStreamSynchronize(s));
   c.ws.release(0);
 }
 
@@ -298,6 +408,7 @@ void m4ri_b200_set_device(int device) {
   if (g.ready && g.device != device) {
     g.ws.destroy();
     cudaStreamDestroy(g.stream);
+    cudaStreamDestroy(g.copy_stream);
     g.ready = false;
   }
   g.device = device;

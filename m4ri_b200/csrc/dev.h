@@ -65,6 +65,19 @@ void multi_release();
 // ---- host scheduler ------------------------------------------------------------------
 struct Workspace;  // bump allocator over one cached device slab
 int  strassen_levels(int m, int k, int n, int cutoff);
-void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s);
+
+// Optional callbacks of the TOP level of the schedule, used by the host path to overlap PCIe
+// transfers with compute: need_*(q) is called before the first kernel that reads quadrant q
+// (0 = 11, 1 = 12, 2 = 21, 3 = 22) of A / B / C-as-addend is enqueued, done_c(q) after the last
+// kernel that writes quadrant q of C.
+struct TopHooks {
+  virtual void need_a(int) {}
+  virtual void need_b(int) {}
+  virtual void need_c(int) {}
+  virtual void done_c(int) {}
+  virtual ~TopHooks() {}
+};
+void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s,
+                  TopHooks *hooks = nullptr);
 
 }  // namespace m4b

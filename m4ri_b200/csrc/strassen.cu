@@ -49,11 +49,15 @@ size_t strassen_workspace_bytes(int m, int k, int n, int levels) {
   return total;
 }
 
-void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s) {
+void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s, TopHooks *hooks) {
   if (C.nrows <= 0 || C.ncols <= 0) return;
+  TopHooks none;
+  TopHooks &hk = hooks ? *hooks : none;
   if (levels == 0) {
+    for (int q = 0; q < 4; ++q) { hk.need_a(q); hk.need_b(q); if (!clear) hk.need_c(q); }
     if (clear) launch_zero(C, s);
     launch_m4rm(C, A, B, s);
+    for (int q = 0; q < 4; ++q) hk.done_c(q);
     return;
   }
   int const m2 = A.nrows / 2, k2 = A.ncols / 2, n2 = B.ncols / 2;
@@ -69,52 +73,75 @@ void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &
   if (clear) {
     // C = A*B, 7 products, 15 adds (strassen.c:111-150)
     DView X = ws.alloc(m2, k2), Y = ws.alloc(k2, n2), P = ws.alloc(m2, n2);
+    hk.need_b(3); hk.need_b(1);
     launch_xor(Y, b22, b12, s);
+    hk.need_a(3); hk.need_a(1);
     launch_xor(X, a22, a12, s);
     strassen_mul(c21, X, Y, lv, true, ws, s);
+    hk.need_a(2);
     launch_xor(X, a22, a21, s);
+    hk.need_b(2);
     launch_xor(Y, b22, b21, s);
     strassen_mul(c22, X, Y, lv, true, ws, s);
     launch_xor(Y, Y, b12, s);
     launch_xor(X, X, a12, s);
     strassen_mul(c11, X, Y, lv, true, ws, s);
+    hk.need_a(0);
     launch_xor(X, X, a11, s);
     strassen_mul(c12, X, b12, lv, true, ws, s);
     launch_xor(c12, c12, c22, s);
     strassen_mul(P, a12, b21, lv, true, ws, s);
     launch_xor(c11, c11, P, s);
     launch_xor(c12, c11, c12, s);
+    hk.done_c(1);
     launch_xor(c11, c21, c11, s);
+    hk.need_b(0);
     launch_xor(Y, Y, b11, s);
     strassen_mul(c21, a21, Y, lv, true, ws, s);
     launch_xor(c21, c11, c21, s);
+    hk.done_c(2);
     launch_xor(c22, c22, c11, s);
+    hk.done_c(3);
     strassen_mul(c11, a11, b11, lv, true, ws, s);
     launch_xor(c11, c11, P, s);
+    hk.done_c(0);
   } else {
     // C ^= A*B, 7 products, 14 adds (strassen.c:436-466)
     DView S = ws.alloc(m2, k2), T = ws.alloc(k2, n2), U = ws.alloc(m2, n2);
+    hk.need_a(3); hk.need_a(2);
     launch_xor(S, a22, a21, s);
+    hk.need_b(3); hk.need_b(2);
     launch_xor(T, b22, b21, s);
     strassen_mul(U, S, T, lv, true, ws, s);
+    hk.need_c(3);
     launch_xor(c22, U, c22, s);
+    hk.need_c(1);
     launch_xor(c12, U, c12, s);
+    hk.need_a(1);
     strassen_mul(U, a12, b21, lv, true, ws, s);
+    hk.need_c(0);
     launch_xor(c11, U, c11, s);
+    hk.need_a(0); hk.need_b(0);
     strassen_mul(c11, a11, b11, lv, false, ws, s);
+    hk.done_c(0);
     launch_xor(S, S, a12, s);
+    hk.need_b(1);
     launch_xor(T, T, b12, s);
     strassen_mul(U, S, T, lv, false, ws, s);
     launch_xor(c12, c12, U, s);
     launch_xor(S, a11, S, s);
     strassen_mul(c12, S, b12, lv, false, ws, s);
+    hk.done_c(1);
     launch_xor(T, b11, T, s);
+    hk.need_c(2);
     strassen_mul(c21, a21, T, lv, false, ws, s);
     launch_xor(S, a22, a12, s);
     launch_xor(T, b22, b12, s);
     strassen_mul(U, S, T, lv, false, ws, s);
     launch_xor(c21, c21, U, s);
+    hk.done_c(2);
     launch_xor(c22, c22, U, s);
+    hk.done_c(3);
   }
   ws.release(mark);
 }
