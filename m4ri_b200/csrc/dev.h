@@ -42,6 +42,8 @@ extern unsigned long long g_kernel_launches;  // counted by every launcher in th
 // ---- leaf: C ^= A*B (M4RM, stream-K persistent kernel) -------------------------------
 // C must already hold the addend (zeros for a plain product).
 void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream);
+// up to 7 products of identical shape in ONE persistent launch (the last Strassen level)
+void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream);
 int  m4rm_num_sms();
 void leaf_profile_begin();
 unsigned long long leaf_profile_end(double *ms, double *bitops);
@@ -51,6 +53,10 @@ void launch_xor(DView C, DView A, DView B, cudaStream_t stream);        // C = A
 void launch_zero(DView C, cudaStream_t stream);                          // C = 0
 void launch_copy(DView C, DView A, cudaStream_t stream);                 // C = A
 void launch_mask_excess(DView C, cudaStream_t stream);                   // clear bits >= ncols of last word(s)
+// fused additions of one Strassen-Winograd node (quadrant order 11, 12, 21, 22)
+void launch_winograd_pre_a(DView const a[4], DView const s_out[4], cudaStream_t stream);
+void launch_winograd_pre_b(DView const b[4], DView const t_out[4], cudaStream_t stream);
+void launch_winograd_post(DView const p[7], DView const c[4], bool accumulate, cudaStream_t stream);
 
 // ---- host <-> device transfers (capi.cu) ----------------------------------------------
 void upload(DView dst, mzd_t const *src, cudaStream_t s);                 // excess bits cleared on device

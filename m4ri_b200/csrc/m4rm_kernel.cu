@@ -45,15 +45,23 @@ constexpr int kSlabBits   = 128;                // K extent of one TMA slab
 constexpr int kStepsPerSlab = kSlabBits / 16;   // 8 steps of 16 A-columns
 constexpr int kBSlabBytes = kSlabBits * kRowBytes;  // 16 KB
 
-struct Params {
-  unsigned long long *C;
-  long long pitchC;     // words
+// One launch multiplies up to kMaxBatch independent products of IDENTICAL shape (the seven products of
+// the last Strassen level): the stream-K unit space simply runs over (problem, tile, slab).
+constexpr int kMaxBatch = 7;
+
+struct alignas(64) BatchArgs {
+  CUtensorMap mapA[kMaxBatch];
+  CUtensorMap mapB[kMaxBatch];
+  unsigned long long *C[kMaxBatch];
+  long long pitchC[kMaxBatch];   // words
   int m;                // rows of A / C
   int nwordsC;          // 64-bit words per C row that may be written
   int tiles_m;
   int tiles_n;
   int slabs;            // ceil(l / 128)
-  long long total_units;  // tiles_m * tiles_n * slabs
+  int nprob;
+  long long units_per_problem;   // tiles_m * tiles_n * slabs
+  long long total_units;         // nprob * units_per_problem
 };
 
 __device__ __forceinline__ uint32_t smem_u32(void const *p) {
@@ -206,7 +214,7 @@ __device__ __forceinline__ void build_step(uint32_t tbuf, uint32_t brows16, int 
 //      extractions for the same number of table lookups.
 template <int TM, int NT, int BW, int MAP>
 __global__ void __launch_bounds__(NT, 1)
-m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p) {
+m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
   using C = Cfg<TM, NT>;
   constexpr int R = C::R;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -241,8 +249,11 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint32_t const lane_off2 = (hi ^ 1) * 64 + c4 * 16;      // MAP 1: the other half of the row
 
   for (long long u = u_begin; u < u_end;) {
-    int const tile  = (int)(u / p.slabs);
-    int const s0    = (int)(u % p.slabs);
+    int const prob  = (int)(u / p.units_per_problem);
+    long long const v = u - (long long)prob * p.units_per_problem;
+    int const tile  = (int)(v / p.slabs);
+    int const s0    = (int)(v % p.slabs);
+    CUtensorMap const *mapA = &p.mapA[prob], *mapB = &p.mapB[prob];
     int nseg        = p.slabs - s0;
     if ((long long)nseg > u_end - u) nseg = (int)(u_end - u);
     int const tm = tile % p.tiles_m, tn = tile / p.tiles_m;
@@ -254,9 +265,9 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_expect_tx(bar, C::kSlabTxBytes);
 #pragma unroll
       for (int part = 0; part < TM / C::kABoxRows; ++part)
-        tma_load_2d(sA + slot * C::kASlabBytes + part * C::kABoxRows * 16, &mapA, (s0 + i) * 4,
+        tma_load_2d(sA + slot * C::kASlabBytes + part * C::kABoxRows * 16, mapA, (s0 + i) * 4,
                     row0 + part * C::kABoxRows, bar);
-      tma_load_2d(sB + slot * kBSlabBytes, &mapB, tn * 32, (s0 + i) * kSlabBits, bar);
+      tma_load_2d(sB + slot * kBSlabBytes, mapB, tn * 32, (s0 + i) * kSlabBits, bar);
     };
 
     if (tid == 0) {
@@ -337,7 +348,7 @@ m4rm_streamk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
           for (int h = 0; h < AW; ++h) {
             int const wcol = tn * (kTileBits / 64) + (MAP == 1 ? (hi ^ h) * 8 + c4 * 2 : c * 2);
-            unsigned long long *dst = p.C + (long long)row * p.pitchC + wcol;
+            unsigned long long *dst = p.C[prob] + (long long)row * p.pitchC[prob] + wcol;
             if (wcol < p.nwordsC) red_xor64(dst, acc[j][h].x, acc[j][h].y);
             if (wcol + 1 < p.nwordsC) red_xor64(dst + 1, acc[j][h].z, acc[j][h].w);
           }
@@ -384,7 +395,7 @@ CUtensorMap make_map(DView V, int box_w32, int box_rows) {
 }
 
 template <int TM, int NT, int BW, int MAP>
-void launch_variant(DView Cv, DView A, DView B, cudaStream_t stream) {
+void launch_variant(int count, DView const *Cv, DView const *A, DView const *B, cudaStream_t stream) {
   using C = Cfg<TM, NT>;
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
   auto kern = m4rm_streamk_kernel<TM, NT, BW, MAP>;
@@ -394,20 +405,26 @@ void launch_variant(DView Cv, DView A, DView B, cudaStream_t stream) {
     M4B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured[dev & 63] = true;
   }
-  Params p;
-  p.C = reinterpret_cast<unsigned long long *>(Cv.data);
-  p.pitchC = Cv.pitch;
-  p.m = A.nrows;
-  p.nwordsC = (Cv.ncols + 63) / 64;
-  p.tiles_m = (A.nrows + TM - 1) / TM;
-  p.tiles_n = (B.ncols + kTileBits - 1) / kTileBits;
-  p.slabs = (A.ncols + kSlabBits - 1) / kSlabBits;
-  p.total_units = (long long)p.tiles_m * p.tiles_n * p.slabs;
-  CUtensorMap mapA = make_map(A, 4, C::kABoxRows);
-  CUtensorMap mapB = make_map(B, 32, kSlabBits);
+  BatchArgs p;
+  p.m = A[0].nrows;
+  p.nwordsC = (Cv[0].ncols + 63) / 64;
+  p.tiles_m = (A[0].nrows + TM - 1) / TM;
+  p.tiles_n = (B[0].ncols + kTileBits - 1) / kTileBits;
+  p.slabs = (A[0].ncols + kSlabBits - 1) / kSlabBits;
+  p.nprob = count;
+  p.units_per_problem = (long long)p.tiles_m * p.tiles_n * p.slabs;
+  p.total_units = p.units_per_problem * count;
+  for (int i = 0; i < count; ++i) {
+    if (A[i].nrows != A[0].nrows || A[i].ncols != A[0].ncols || B[i].ncols != B[0].ncols)
+      die("m4ri_b200: batched leaf needs identical shapes\n");
+    p.C[i] = reinterpret_cast<unsigned long long *>(Cv[i].data);
+    p.pitchC[i] = Cv[i].pitch;
+    p.mapA[i] = make_map(A[i], 4, C::kABoxRows);
+    p.mapB[i] = make_map(B[i], 32, kSlabBits);
+  }
   long long grid = m4rm_num_sms();
   if (grid > p.total_units) grid = p.total_units;
-  kern<<<(unsigned)grid, NT, C::kSmemBytes, stream>>>(mapA, mapB, p);
+  kern<<<(unsigned)grid, NT, C::kSmemBytes, stream>>>(p);
   M4B_CUDA(cudaGetLastError());
   ++g_kernel_launches;
 }
@@ -456,8 +473,9 @@ int m4rm_num_sms() {
   return sms;
 }
 
-void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) {
-  if (A.nrows <= 0 || A.ncols <= 0 || B.ncols <= 0) return;   // empty product: C unchanged
+void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream) {
+  if (count <= 0 || A[0].nrows <= 0 || A[0].ncols <= 0 || B[0].ncols <= 0) return;   // empty product: C unchanged
+  if (count > kMaxBatch) die("m4ri_b200: batch of %d leaf products exceeds %d\n", count, kMaxBatch);
   std::pair<cudaEvent_t, cudaEvent_t> *ev = nullptr;
   if (g_prof.on) {
     if (g_prof.used == g_prof.pool.size()) {
@@ -467,7 +485,7 @@ void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) {
       g_prof.pool.push_back(e);
     }
     ev = &g_prof.pool[g_prof.used++];
-    g_prof.bitops += 2.0 * A.nrows * (double)A.ncols * B.ncols;
+    g_prof.bitops += 2.0 * count * A[0].nrows * (double)A[0].ncols * B[0].ncols;
     M4B_CUDA(cudaEventRecord(ev->first, stream));
   }
   static int variant = -1;
@@ -475,17 +493,19 @@ void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) {
     char const *env = getenv("M4RI_B200_VARIANT");   // tuning/debug only
     variant = env ? atoi(env) : 0;
   }
-  if (A.nrows <= 256)
-    launch_variant<256, 256, 4, 1>(C, A, B, stream);
+  if (A[0].nrows <= 256)
+    launch_variant<256, 256, 4, 1>(count, C, A, B, stream);
   else if (variant == 1)
-    launch_variant<1024, 256, 4, 0>(C, A, B, stream);
+    launch_variant<1024, 256, 4, 0>(count, C, A, B, stream);
   else if (variant == 2)
-    launch_variant<1024, 256, 16, 0>(C, A, B, stream);
+    launch_variant<1024, 256, 16, 0>(count, C, A, B, stream);
   else if (variant == 3)
-    launch_variant<1024, 256, 16, 1>(C, A, B, stream);
+    launch_variant<1024, 256, 16, 1>(count, C, A, B, stream);
   else
-    launch_variant<1024, 256, 4, 1>(C, A, B, stream);
+    launch_variant<1024, 256, 4, 1>(count, C, A, B, stream);
   if (ev) M4B_CUDA(cudaEventRecord(ev->second, stream));
 }
+
+void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) { launch_m4rm_batch(1, &C, &A, &B, stream); }
 
 }  // namespace m4b

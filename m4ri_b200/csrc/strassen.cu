@@ -40,13 +40,62 @@ int strassen_levels(int m, int k, int n, int cutoff) {
   return levels;
 }
 
+// Workspace: the top level keeps the reference's in-place sequence (3 quarter-size temporaries), every
+// level below is a fused Winograd node (4 + 4 operand sums and 7 product temporaries).
 size_t strassen_workspace_bytes(int m, int k, int n, int levels) {
   size_t total = 0;
   for (int lv = 0; lv < levels; ++lv) {
     m /= 2; k /= 2; n /= 2;
-    total += Workspace::bytes_for(m, k) + Workspace::bytes_for(k, n) + Workspace::bytes_for(m, n);
+    size_t const a = Workspace::bytes_for(m, k), b = Workspace::bytes_for(k, n), c = Workspace::bytes_for(m, n);
+    total += lv == 0 ? a + b + c : 4 * a + 4 * b + Workspace::bytes_for(7 * m, n);
   }
   return total;
+}
+
+static void quadrants(DView const &V, DView q[4]) {
+  int const r2 = V.nrows / 2, c2 = V.ncols / 2;
+  q[0] = V.sub(0, 0, r2, c2);
+  q[1] = V.sub(0, c2, r2, 2 * c2);
+  q[2] = V.sub(r2, 0, 2 * r2, c2);
+  q[3] = V.sub(r2, c2, 2 * r2, 2 * c2);
+}
+
+// One Strassen-Winograd node below the top level, three kinds of launches only:
+//   pre   S1..S4 / T1..T4 from the quadrants of A / B         (2 fused element-wise launches)
+//   mul   P1..P7; when the children are leaves ALL SEVEN run in one persistent stream-K launch
+//   post  C11 C12 C21 C22 from P1..P7                          (1 fused element-wise launch)
+// Same products as strassen.c's sequence (Winograd's 7-product form), different bookkeeping: more
+// temporaries (HBM is 180 GB), a third of the element-wise traffic and 3-4 launches instead of 29.
+static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s) {
+  if (levels == 0) {
+    if (clear) launch_zero(C, s);
+    launch_m4rm(C, A, B, s);
+    return;
+  }
+  DView a[4], b[4], c[4];
+  quadrants(A, a);
+  quadrants(B, b);
+  quadrants(C, c);
+  int const m2 = a[0].nrows, k2 = a[0].ncols, n2 = b[0].ncols;
+  size_t const mark = ws.mark();
+  DView S[4], T[4], P[7];
+  for (int i = 0; i < 4; ++i) S[i] = ws.alloc(m2, k2);
+  for (int i = 0; i < 4; ++i) T[i] = ws.alloc(k2, n2);
+  DView const Pall = ws.alloc(7 * m2, n2);
+  for (int i = 0; i < 7; ++i) P[i] = Pall.sub(i * m2, 0, (i + 1) * m2, n2);
+  launch_winograd_pre_a(a, S, s);
+  launch_winograd_pre_b(b, T, s);
+  //                   P1     P2     P3     P4     P5     P6     P7
+  DView const X[7] = {a[0], a[1], S[3], a[3], S[0], S[1], S[2]};
+  DView const Y[7] = {b[0], b[2], b[3], T[3], T[0], T[1], T[2]};
+  if (levels == 1) {
+    launch_zero(Pall, s);
+    launch_m4rm_batch(7, P, X, Y, s);
+  } else {
+    for (int i = 0; i < 7; ++i) winograd_node(P[i], X[i], Y[i], levels - 1, true, ws, s);
+  }
+  launch_winograd_post(P, c, !clear, s);
+  ws.release(mark);
 }
 
 void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s, TopHooks *hooks) {
@@ -77,32 +126,32 @@ void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &
     launch_xor(Y, b22, b12, s);
     hk.need_a(3); hk.need_a(1);
     launch_xor(X, a22, a12, s);
-    strassen_mul(c21, X, Y, lv, true, ws, s);
+    winograd_node(c21, X, Y, lv, true, ws, s);
     hk.need_a(2);
     launch_xor(X, a22, a21, s);
     hk.need_b(2);
     launch_xor(Y, b22, b21, s);
-    strassen_mul(c22, X, Y, lv, true, ws, s);
+    winograd_node(c22, X, Y, lv, true, ws, s);
     launch_xor(Y, Y, b12, s);
     launch_xor(X, X, a12, s);
-    strassen_mul(c11, X, Y, lv, true, ws, s);
+    winograd_node(c11, X, Y, lv, true, ws, s);
     hk.need_a(0);
     launch_xor(X, X, a11, s);
-    strassen_mul(c12, X, b12, lv, true, ws, s);
+    winograd_node(c12, X, b12, lv, true, ws, s);
     launch_xor(c12, c12, c22, s);
-    strassen_mul(P, a12, b21, lv, true, ws, s);
+    winograd_node(P, a12, b21, lv, true, ws, s);
     launch_xor(c11, c11, P, s);
     launch_xor(c12, c11, c12, s);
     hk.done_c(1);
     launch_xor(c11, c21, c11, s);
     hk.need_b(0);
     launch_xor(Y, Y, b11, s);
-    strassen_mul(c21, a21, Y, lv, true, ws, s);
+    winograd_node(c21, a21, Y, lv, true, ws, s);
     launch_xor(c21, c11, c21, s);
     hk.done_c(2);
     launch_xor(c22, c22, c11, s);
     hk.done_c(3);
-    strassen_mul(c11, a11, b11, lv, true, ws, s);
+    winograd_node(c11, a11, b11, lv, true, ws, s);
     launch_xor(c11, c11, P, s);
     hk.done_c(0);
   } else {
@@ -112,32 +161,32 @@ void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &
     launch_xor(S, a22, a21, s);
     hk.need_b(3); hk.need_b(2);
     launch_xor(T, b22, b21, s);
-    strassen_mul(U, S, T, lv, true, ws, s);
+    winograd_node(U, S, T, lv, true, ws, s);
     hk.need_c(3);
     launch_xor(c22, U, c22, s);
     hk.need_c(1);
     launch_xor(c12, U, c12, s);
     hk.need_a(1);
-    strassen_mul(U, a12, b21, lv, true, ws, s);
+    winograd_node(U, a12, b21, lv, true, ws, s);
     hk.need_c(0);
     launch_xor(c11, U, c11, s);
     hk.need_a(0); hk.need_b(0);
-    strassen_mul(c11, a11, b11, lv, false, ws, s);
+    winograd_node(c11, a11, b11, lv, false, ws, s);
     hk.done_c(0);
     launch_xor(S, S, a12, s);
     hk.need_b(1);
     launch_xor(T, T, b12, s);
-    strassen_mul(U, S, T, lv, false, ws, s);
+    winograd_node(U, S, T, lv, false, ws, s);
     launch_xor(c12, c12, U, s);
     launch_xor(S, a11, S, s);
-    strassen_mul(c12, S, b12, lv, false, ws, s);
+    winograd_node(c12, S, b12, lv, false, ws, s);
     hk.done_c(1);
     launch_xor(T, b11, T, s);
     hk.need_c(2);
-    strassen_mul(c21, a21, T, lv, false, ws, s);
+    winograd_node(c21, a21, T, lv, false, ws, s);
     launch_xor(S, a22, a12, s);
     launch_xor(T, b22, b12, s);
-    strassen_mul(U, S, T, lv, false, ws, s);
+    winograd_node(U, S, T, lv, false, ws, s);
     launch_xor(c21, c21, U, s);
     hk.done_c(2);
     launch_xor(c22, c22, U, s);

@@ -318,3 +318,67 @@ def test_c_program_linked_against_both_libraries(tmp_path):
     p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "All tests passed." in p.stdout
+
+
+def test_fuzz_random_shapes_windows_and_entry_points(lib):
+    """Seeded fuzz over shapes the fixed lists do not hit: every entry point, random dims from 1 to
+    ~2500 (biased to word/tile boundaries +-1), A/B/C randomly windows at random word offsets."""
+    rng = np.random.default_rng(20261017)
+    edges = [1, 2, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049]
+    fns = ["mzd_mul", "mzd_addmul", "mzd_mul_m4rm", "mzd_addmul_m4rm", "_mzd_mul_m4rm", "_mzd_mul_even",
+           "_mzd_addmul_even", "_mzd_addmul", "mzd_mul_mp", "mzd_addmul_mp"]
+    O = H.oracle()
+
+    def dim():
+        return int(rng.choice(edges)) if rng.random() < 0.5 else int(rng.integers(1, 2500))
+
+    def operand(rows, cols):
+        if rng.random() < 0.5:
+            M = H.new(rows, cols)
+            H.storage(M)[:, :] = rng.integers(0, 2**64, size=H.storage(M).shape, dtype=np.uint64)
+            H.storage(M)[:, M.contents.width - 1] &= np.uint64(M.contents.high_bitmask)
+            H.storage(M)[:, M.contents.width:] = 0
+            return None, M
+        off_w, off_r = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+        P = H.new(rows + off_r + 2, (cols + 63) // 64 * 64 + 64 * (off_w + 1))
+        H.storage(P)[:, :] = rng.integers(0, 2**64, size=H.storage(P).shape, dtype=np.uint64)
+        return P, H.window(P, off_r, 64 * off_w, off_r + rows, 64 * off_w + cols)
+
+    for it in range(60):
+        m, l, n = dim(), dim(), dim()
+        fn = fns[it % len(fns)]
+        cutoff = int(rng.choice([0, 64, 128, 256, 512, 1024]))
+        PA, A = operand(m, l)
+        PB, B = operand(l, n)
+        PC, C = operand(m, n)
+        ref_parent = H.clone(PC) if PC is not None else None
+        if ref_parent is not None:
+            H.storage(ref_parent)[:, :] = H.storage(PC)
+            Cw = H.window(ref_parent, 0, 0, 1, 1)  # placeholder, replaced below
+            H.free(Cw)
+            d = C.contents
+            off_words = (ctypes.addressof(d.data.contents) - ctypes.addressof(PC.contents.data.contents)) // 8
+            r0, w0 = divmod(off_words, PC.contents.rowstride)
+            Cw = H.window(ref_parent, r0, 64 * w0, r0 + m, 64 * w0 + n)
+        else:
+            Cw = H.clone(C)
+        accumulate = "add" in fn
+        if accumulate:
+            O.orc_addmul(Cw, A, B, 0)
+        else:
+            O.orc_mul(Cw, A, B, 0)
+        if fn == "_mzd_mul_m4rm":
+            lib._mzd_mul_m4rm(C, A, B, 0, 1)
+        else:
+            getattr(lib, fn)(C, A, B, cutoff)
+        if PC is not None:
+            assert np.array_equal(H.storage(PC), H.storage(ref_parent)), (it, fn, m, l, n, cutoff)
+        else:
+            assert np.array_equal(H.storage(C), H.storage(Cw)), (it, fn, m, l, n, cutoff)
+        for parent, win in ((PA, A), (PB, B), (PC, C)):
+            H.free(win)
+            if parent is not None:
+                H.free(parent)
+        H.free(Cw)
+        if ref_parent is not None:
+            H.free(ref_parent)
