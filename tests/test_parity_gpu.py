@@ -272,13 +272,15 @@ def _unpack(words, n):
     return b[:n].astype(bool)
 
 
-@pytest.mark.parametrize("shape,cutoff,fn", [((16384, 16384, 16384), 0, "mzd_mul_m4rm"),
-                                             ((16384, 16384, 16384), 4096, "mzd_mul"),
-                                             ((4100, 20000, 9000), 2048, "mzd_mul")])
-def test_full_size_freivalds_and_linearity(lib, shape, cutoff, fn):
+@pytest.mark.parametrize("shape,cutoff,fn,nvec", [((16384, 16384, 16384), 0, "mzd_mul_m4rm", 40),   # BASELINE config 2
+                                                  ((16384, 16384, 16384), 4096, "mzd_mul", 40),
+                                                  ((4100, 20000, 9000), 2048, "mzd_mul", 40),
+                                                  ((65536, 65536, 65536), 0, "mzd_mul", 16),          # config 3
+                                                  ((32768, 131072, 32768), 0, "mzd_mul", 16)])        # config 5 shape
+def test_full_size_freivalds_and_linearity(lib, shape, cutoff, fn, nvec):
     """Sizes the oracle cannot finish quickly: size-independent properties.
-    (1) Freivalds over GF(2): for random x, (A*B)x == A(Bx), 40 vectors -> error prob 2^-40.
-    (2) linearity: (A ^ A')*B == A*B ^ A'*B through mzd_addmul."""
+    (1) Freivalds over GF(2): for random x, (A*B)x == A(Bx), nvec vectors -> error prob 2^-nvec.
+    (2) linearity: (A ^ A')*B == A*B ^ A'*B through mzd_addmul (config 5 is an addmul)."""
     m, l, n = shape
     A, B = H.new(m, l), H.new(l, n)
     _fill_fast(A, 10); _fill_fast(B, 20)
@@ -286,7 +288,7 @@ def test_full_size_freivalds_and_linearity(lib, shape, cutoff, fn):
     getattr(lib, fn)(C, A, B, cutoff)
     Aw, Bw, Cw = m4ri_b200.valid_words(A), m4ri_b200.valid_words(B), m4ri_b200.valid_words(C)
     rng = np.random.default_rng(3)
-    for _ in range(40):
+    for _ in range(nvec):
         x = rng.integers(0, 2, size=n).astype(bool)
         bx = _gf2_matvec_rows(Bw, _pack(x))
         abx = _gf2_matvec_rows(Aw, _pack(bx))
