@@ -47,6 +47,12 @@ struct Ctx {
   char         last_path[64] = "none";
 };
 Ctx g;
+unsigned long long g_products = 0;   // host-path products served (reported at exit with M4RI_B200_REPORT=1)
+
+void report_at_exit() {
+  fprintf(stderr, "m4ri_b200: served %llu products with %llu CUDA kernel launches (last path %s)\n", g_products,
+          g_kernel_launches, g.last_path);
+}
 
 Ctx &ctx() {
   if (!g.ready) {
@@ -58,6 +64,7 @@ Ctx &ctx() {
     M4B_CUDA(cudaGetDevice(&g.device));
     M4B_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     M4B_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    if (getenv("M4RI_B200_REPORT")) atexit(report_at_exit);
     if (!g.default_cutoff) {
       char const *env = getenv("M4RI_B200_CUTOFF");
       g.default_cutoff = env && atoi(env) > 0 ? atoi(env) : kBuiltinCutoff;
@@ -236,6 +243,7 @@ void host_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool cle
   Ctx &c = ctx();
   int const m = A->nrows, l = A->ncols, n = B->ncols;
   if (m == 0 || n == 0) return;
+  ++g_products;
   int const levels = (strassen && l > 0) ? strassen_levels(m, l, n, cutoff) : 0;
   int const mp = round_up(m, 1 << levels), lp = round_up(l > 0 ? l : 1, 128 << levels), np = round_up(n, 128 << levels);
   snprintf(c.last_path, sizeof c.last_path, levels ? "strassen:%d" : "m4rm", levels);
