@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 BIN_DIR = os.path.join(H.ORACLE_DIR, "_ref", "tests")
 # programs whose code path reaches the multiplication symbols (the others still must pass untouched)
 USES_MUL = {"test_multiplication", "test_smallops", "test_trsm", "test_ple", "test_pluq", "test_solve",
-            "test_kernel", "test_invert", "test_elimination"}
+            "test_kernel", "test_invert"}
 ALL = ["test_multiplication", "test_smallops", "test_elimination", "test_trsm", "test_ple", "test_pluq", "test_solve",
        "test_kernel", "test_invert", "test_random", "test_transpose", "test_colswap", "test_misc", "test_alignment",
        "test_djb"]
