@@ -13,18 +13,19 @@
 //     C with red.global.xor — exact, order independent, no second pass.
 //   * C tile = TM x 1024 bits lives in registers for the whole K range of a segment
 //     (C is touched once per segment instead of once per 64 columns of A as on the CPU).
-//   * A table row is exactly 128 B = all 32 banks, so the 8 lanes that own one C row fetch one
-//     whole row with a conflict-free LDS.128; one warp instruction serves 4 C rows.
+//   * A table row is exactly 128 B = all 32 banks; the lookup mapping (see the kernel) makes every
+//     quarter-warp pass of an LDS.128 read 128 conflict-free bytes; one warp instruction serves 8 C rows.
 //   * k = 8 bits per table, 2 tables (16 columns of A) per step, tables double buffered: the
-//     tables for step i+1 are built (Gray-code walk, one STS.128 per entry, no table reads)
+//     tables for step i+1 are built (Gray-code walk, one STS.32 wavefront per entry, no table reads)
 //     while step i's lookups run; one __syncthreads per step.
 //   * A (TM x 128 bit) and B (128 x 1024 bit) slabs arrive by TMA (cp.async.bulk.tensor.2d)
 //     into a 2-deep ring guarded by mbarriers; out-of-range rows/columns are zero-filled by
 //     the TMA unit, which is what makes ragged m / l / n edges free.
+//   * Up to seven products of identical shape (the last Strassen level) share ONE launch.
 //
-// Binding resource: shared-memory bandwidth (128 B/clk/SM): per step and per warp 32 lookups
-// (4 wavefronts each) + 8 table stores (4 each) + 8 B-row loads + 8 A loads = 176 wavefronts
-// for 2*16*64*1024 bit-ops.  See DESIGN.md for the roofline derived from this.
+// Binding resource: shared-memory bandwidth (128 B/clk/SM): per step and CTA 2048 lookup wavefronts
+// + 512 table-store + 64 B-row + 64 A-word wavefronts for 2*16*1024*1024 bit-ops; ncu shows the
+// l1tex data pipe 93 % busy.  See DESIGN.md §4 for the roofline derived from this.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -103,9 +104,6 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -113,19 +111,12 @@ __device__ __forceinline__ void red_xor64(unsigned long long *p, uint32_t lo, ui
   unsigned long long v = (static_cast<unsigned long long>(hi) << 32) | lo;
   asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void xor4(uint4 &a, uint4 const &b) { a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w; }
-__device__ __forceinline__ void xor4m(uint4 &a, uint4 const &b, uint32_t m) {
-  a.x ^= b.x & m; a.y ^= b.y & m; a.z ^= b.z & m; a.w ^= b.w & m;
-}
 
 template <int TM, int NT>
 struct Cfg {
   static constexpr int kWarps      = NT / 32;
   static constexpr int kRowsPerWarp = TM / kWarps;
-  static constexpr int R           = kRowsPerWarp / 4;   // C rows held per thread
-  static constexpr int kGroups     = NT / 8;             // 8-lane groups that build table entries
-  static constexpr int kEntries    = 512 / kGroups;      // entries each group builds per step
-  static constexpr int kGrayBits   = kEntries == 8 ? 3 : (kEntries == 16 ? 4 : (kEntries == 4 ? 2 : -1));
+  static constexpr int R           = kRowsPerWarp / 4;   // 2 x rows held per thread (each row as two 16-byte pieces)
   static constexpr int kASlabBytes = TM * 16;
   static constexpr int kABoxRows   = TM < 256 ? TM : 256;
   static constexpr int kOffTables  = 0;
@@ -134,48 +125,18 @@ struct Cfg {
   static constexpr int kOffBar     = kOffB + 2 * kBSlabBytes;
   static constexpr int kSmemBytes  = kOffBar + 64;
   static constexpr uint32_t kSlabTxBytes = kASlabBytes + kBSlabBytes;
-  static_assert(kGrayBits > 0, "unsupported thread count");
   static_assert(R >= 2 && kRowsPerWarp % 8 == 0, "bad tile shape");
 };
 
-// Build the two 256-entry tables of one step from 16 rows of the B slab.
-// Thread (g = tid/8, c = tid%8): table t = g / (groups/2), high index bits h, 16-byte column
-// chunk c.  base = XOR of the B rows selected by h; the low kGrayBits index bits are walked in
-// reflected Gray order so each further entry costs one 128-bit XOR and one STS.128 —
-// the same trick as mzd_make_table, but per thread and without reading the table back.
+// Build the two 256-entry tables of one step from 16 rows of the B slab (replaces mzd_make_table).
+// The 32 lanes of a warp own the 32 words of one table row (LDS.32 / STS.32 = exactly one 128-byte
+// wavefront each); a warp owns 512/warps consecutive entries of one table: base = XOR of the B rows
+// selected by the high index bits, then the low GB index bits are walked in reflected Gray order so
+// every further entry costs one XOR and one store — the trick of mzd_make_table, but without ever
+// reading the table back.  (An earlier 8-lane x 16-byte mapping paid 4 wavefronts per B-row LDS.128
+// because every quarter-warp re-read the same 128 bytes.)
 template <int TM, int NT>
 __device__ __forceinline__ void build_tables(uint32_t tbuf, uint32_t brows16, int tid) {
-  using C = Cfg<TM, NT>;
-  constexpr int GB = C::kGrayBits;
-  int const g = tid >> 3, c = tid & 7;
-  int const t = g / (C::kGroups / 2);
-  int const h = g % (C::kGroups / 2);                       // index bits GB..7
-  uint32_t const src = brows16 + (t * 8) * kRowBytes + c * 16;
-  uint4 low[GB];
-#pragma unroll
-  for (int b = 0; b < GB; ++b) low[b] = lds128(src + b * kRowBytes);
-  uint4 e = make_uint4(0, 0, 0, 0);
-#pragma unroll
-  for (int b = GB; b < 8; ++b) {
-    uint4 v = lds128(src + b * kRowBytes);
-    xor4m(e, v, 0u - ((h >> (b - GB)) & 1u));
-  }
-  uint32_t const dst = tbuf + t * kTableBytes + (h << GB) * kRowBytes + c * 16;
-  sts128(dst, e);
-#pragma unroll
-  for (int i = 1; i < (1 << GB); ++i) {
-    // bit that changes between gray(i-1) and gray(i) = ctz(i); spelled so it folds after unrolling
-    xor4(e, low[(i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : 3]);
-    sts128(dst + (i ^ (i >> 1)) * kRowBytes, e);
-  }
-}
-
-// Same tables, warp-per-entry mapping: the 32 lanes of a warp own the 32 words of one table row
-// (LDS.32 / STS.32 = exactly one 128-byte wavefront each), a warp walks 512/warps entries in Gray
-// order.  Versus the 8-lane mapping this removes the 4-pass cost of LDS.128 for the B rows (every
-// quarter-warp re-read the same 128 bytes): 8 wavefronts of B loads per warp and step instead of 32.
-template <int TM, int NT>
-__device__ __forceinline__ void build_tables_w32(uint32_t tbuf, uint32_t brows16, int tid) {
   constexpr int W  = NT / 32;
   constexpr int E  = 512 / W;                                   // entries per warp and step
   constexpr int GB = E == 64 ? 6 : (E == 32 ? 5 : (E == 16 ? 4 : -1));
@@ -198,21 +159,13 @@ __device__ __forceinline__ void build_tables_w32(uint32_t tbuf, uint32_t brows16
   }
 }
 
-template <int TM, int NT, int BW>
-__device__ __forceinline__ void build_step(uint32_t tbuf, uint32_t brows16, int tid) {
-  if (BW == 4) build_tables_w32<TM, NT>(tbuf, brows16, tid);
-  else         build_tables<TM, NT>(tbuf, brows16, tid);
-}
-
-// MAP selects the lane -> C-element mapping of the lookup loop:
-//   0: 8 lanes x 16 B own one C row (1024 bits); a warp LDS.128 serves 4 rows.
-//   1: 4 lanes x 16 B own one HALF row; lanes 0-3 of a quarter-warp take one row, lanes 4-7 the next,
-//      and the two halves are fetched by two LDS.128 with the halves swapped between the lane groups, so
-//      every quarter-warp pass still reads 128 contiguous-bank bytes (low half of one table row + high
-//      half of another: conflict-free).  A warp instruction serves 8 rows, so a thread holds half as
-//      many rows (R/2) of twice the width: half the A-index registers, half the A-word loads and index
-//      extractions for the same number of table lookups.
-template <int TM, int NT, int BW, int MAP>
+// Lane -> C-element mapping of the lookup loop: 4 lanes x 16 B own one HALF row of C (512 bits); in each
+// quarter-warp lanes 0-3 take one C row and lanes 4-7 the next, and the two halves of the rows are
+// fetched by two LDS.128 with the halves swapped between the lane groups, so every quarter-warp pass
+// reads the low 64 B of one table row and the high 64 B of another: all 32 banks, conflict-free.
+// A warp instruction serves 8 rows; a thread holds R/2 rows of 2 x 16 B.  (The obvious mapping — 8
+// lanes own one full row — needs twice the A-index registers, loads and extractions per lookup.)
+template <int TM, int NT>
 __global__ void __launch_bounds__(NT, 1)
 m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
   using C = Cfg<TM, NT>;
@@ -225,10 +178,9 @@ m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
   uint32_t const sBar = sbase + C::kOffBar;     // two 8-byte mbarriers
 
   int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int const q = lane >> 3, c = lane & 7;
-  int const hi = (lane >> 2) & 1, c4 = lane & 3;          // MAP 1: row parity within the quarter, 16 B chunk of a half row
-  constexpr int RT = MAP == 1 ? R / 2 : R;                 // rows per thread
-  constexpr int AW = MAP == 1 ? 2 : 1;                     // uint4 accumulators per row
+  int const q = lane >> 3;
+  int const hi = (lane >> 2) & 1, c4 = lane & 3;          // row parity within the quarter-warp, 16 B chunk of a half row
+  constexpr int RT = R / 2;                                // rows per thread
 
   if (tid == 0) {
     mbar_init(sBar, 1);
@@ -242,11 +194,10 @@ m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
   long long const u_end   = p.total_units * (long long)(blockIdx.x + 1) / gridDim.x;
   uint32_t parity0 = 0, parity1 = 0;             // phase of each ring slot
 
-  uint32_t const a_row_off = MAP == 1 ? (warp * C::kRowsPerWarp + q * 2 + hi) * 16   // first A row of this lane group
-                                      : (warp * C::kRowsPerWarp + q) * 16;
-  uint32_t const a_row_step = MAP == 1 ? 128 : 64;         // 8 (4) rows further per j
-  uint32_t const lane_off  = MAP == 1 ? hi * 64 + c4 * 16 : c * 16;
-  uint32_t const lane_off2 = (hi ^ 1) * 64 + c4 * 16;      // MAP 1: the other half of the row
+  uint32_t const a_row_off = (warp * C::kRowsPerWarp + q * 2 + hi) * 16;   // first A row of this lane
+  uint32_t const a_row_step = 128;                         // 8 rows further per j
+  uint32_t const lane_off  = hi * 64 + c4 * 16;            // this lane's half of the table row ...
+  uint32_t const lane_off2 = (hi ^ 1) * 64 + c4 * 16;      // ... and the other half
 
   for (long long u = u_begin; u < u_end;) {
     int const prob  = (int)(u / p.units_per_problem);
@@ -275,15 +226,13 @@ m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
       if (nseg > 1) issue(1);
     }
 
-    uint4 acc[RT][AW];
+    uint4 acc[RT][2];
 #pragma unroll
-    for (int j = 0; j < RT; ++j)
-#pragma unroll
-      for (int h = 0; h < AW; ++h) acc[j][h] = make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < RT; ++j) acc[j][0] = acc[j][1] = make_uint4(0, 0, 0, 0);
 
     mbar_wait(sBar, parity0);
     parity0 ^= 1;
-    build_step<TM, NT, BW>(sTab, sB, tid);
+    build_tables<TM, NT>(sTab, sB, tid);
     __syncthreads();
 
     for (int i = 0; i < nseg; ++i) {
@@ -302,11 +251,11 @@ m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
           uint32_t const tnext = sTab + (sub ^ 1) * kStepBufBytes;
           // ---- build tables for the next step into the other buffer ----
           if (step < kStepsPerSlab - 1) {
-            build_step<TM, NT, BW>(tnext, bS + (step + 1) * 16 * kRowBytes, tid);
+            build_tables<TM, NT>(tnext, bS + (step + 1) * 16 * kRowBytes, tid);
           } else if (i + 1 < nseg) {
             if (slot == 0) { mbar_wait(sBar + 8, parity1); parity1 ^= 1; }
             else           { mbar_wait(sBar, parity0);     parity0 ^= 1; }
-            build_step<TM, NT, BW>(tnext, sB + (slot ^ 1) * kBSlabBytes, tid);
+            build_tables<TM, NT>(tnext, sB + (slot ^ 1) * kBSlabBytes, tid);
           }
           // ---- lookups: acc[j] ^= T0[a byte 2*sub] ^ T1[a byte 2*sub+1] ----
           // (rows past m read zero-filled A bits -> table row 0 = zeros; no branch needed)
@@ -322,14 +271,12 @@ m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
             acc[j][0].y ^= v0.y ^ v1.y;
             acc[j][0].z ^= v0.z ^ v1.z;
             acc[j][0].w ^= v0.w ^ v1.w;
-            if (MAP == 1) {
-              uint4 const w0 = lds128(u0 + i0 * kRowBytes);
-              uint4 const w1 = lds128(u1 + i1 * kRowBytes);
-              acc[j][AW - 1].x ^= w0.x ^ w1.x;
-              acc[j][AW - 1].y ^= w0.y ^ w1.y;
-              acc[j][AW - 1].z ^= w0.z ^ w1.z;
-              acc[j][AW - 1].w ^= w0.w ^ w1.w;
-            }
+            uint4 const w0 = lds128(u0 + i0 * kRowBytes);
+            uint4 const w1 = lds128(u1 + i1 * kRowBytes);
+            acc[j][1].x ^= w0.x ^ w1.x;
+            acc[j][1].y ^= w0.y ^ w1.y;
+            acc[j][1].z ^= w0.z ^ w1.z;
+            acc[j][1].w ^= w0.w ^ w1.w;
           }
           __syncthreads();
         }
@@ -340,14 +287,14 @@ m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
 
     // ---- merge the partial tile into C (exact: XOR is associative and commutative) ----
     {
-      int const rbase = row0 + warp * C::kRowsPerWarp + (MAP == 1 ? q * 2 + hi : q);
+      int const rbase = row0 + warp * C::kRowsPerWarp + q * 2 + hi;
 #pragma unroll
       for (int j = 0; j < RT; ++j) {
-        int const row = rbase + (MAP == 1 ? 8 : 4) * j;
+        int const row = rbase + 8 * j;
         if (row < p.m) {
 #pragma unroll
-          for (int h = 0; h < AW; ++h) {
-            int const wcol = tn * (kTileBits / 64) + (MAP == 1 ? (hi ^ h) * 8 + c4 * 2 : c * 2);
+          for (int h = 0; h < 2; ++h) {
+            int const wcol = tn * (kTileBits / 64) + (hi ^ h) * 8 + c4 * 2;
             unsigned long long *dst = p.C[prob] + (long long)row * p.pitchC[prob] + wcol;
             if (wcol < p.nwordsC) red_xor64(dst, acc[j][h].x, acc[j][h].y);
             if (wcol + 1 < p.nwordsC) red_xor64(dst + 1, acc[j][h].z, acc[j][h].w);
@@ -394,11 +341,11 @@ CUtensorMap make_map(DView V, int box_w32, int box_rows) {
   return map;
 }
 
-template <int TM, int NT, int BW, int MAP>
+template <int TM, int NT>
 void launch_variant(int count, DView const *Cv, DView const *A, DView const *B, cudaStream_t stream) {
   using C = Cfg<TM, NT>;
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
-  auto kern = m4rm_streamk_kernel<TM, NT, BW, MAP>;
+  auto kern = m4rm_streamk_kernel<TM, NT>;
   int dev = 0;
   M4B_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
@@ -488,21 +435,10 @@ void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B
     g_prof.bitops += 2.0 * count * A[0].nrows * (double)A[0].ncols * B[0].ncols;
     M4B_CUDA(cudaEventRecord(ev->first, stream));
   }
-  static int variant = -1;
-  if (variant < 0) {
-    char const *env = getenv("M4RI_B200_VARIANT");   // tuning/debug only
-    variant = env ? atoi(env) : 0;
-  }
   if (A[0].nrows <= 256)
-    launch_variant<256, 256, 4, 1>(count, C, A, B, stream);
-  else if (variant == 1)
-    launch_variant<1024, 256, 4, 0>(count, C, A, B, stream);
-  else if (variant == 2)
-    launch_variant<1024, 256, 16, 0>(count, C, A, B, stream);
-  else if (variant == 3)
-    launch_variant<1024, 256, 16, 1>(count, C, A, B, stream);
+    launch_variant<256, 256>(count, C, A, B, stream);     // short operands: 256-row tiles
   else
-    launch_variant<1024, 256, 4, 1>(count, C, A, B, stream);
+    launch_variant<1024, 256>(count, C, A, B, stream);
   if (ev) M4B_CUDA(cudaEventRecord(ev->second, stream));
 }
 

@@ -40,14 +40,13 @@ int strassen_levels(int m, int k, int n, int cutoff) {
   return levels;
 }
 
-// Workspace: the top level keeps the reference's in-place sequence (3 quarter-size temporaries), every
-// level below is a fused Winograd node (4 + 4 operand sums and 7 product temporaries).
+// Workspace: every level is sized as a fused Winograd node (4 + 4 operand sums and 7 product
+// temporaries); the in-place top level of the host path (3 quarter-size temporaries) needs less.
 size_t strassen_workspace_bytes(int m, int k, int n, int levels) {
   size_t total = 0;
   for (int lv = 0; lv < levels; ++lv) {
     m /= 2; k /= 2; n /= 2;
-    size_t const a = Workspace::bytes_for(m, k), b = Workspace::bytes_for(k, n), c = Workspace::bytes_for(m, n);
-    total += lv == 0 ? a + b + c : 4 * a + 4 * b + Workspace::bytes_for(7 * m, n);
+    total += 4 * Workspace::bytes_for(m, k) + 4 * Workspace::bytes_for(k, n) + Workspace::bytes_for(7 * m, n);
   }
   return total;
 }
@@ -100,8 +99,11 @@ static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Wor
 
 void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s, TopHooks *hooks) {
   if (C.nrows <= 0 || C.ncols <= 0) return;
-  TopHooks none;
-  TopHooks &hk = hooks ? *hooks : none;
+  if (!hooks) {   // device-resident operands: no transfers to overlap, every level is a fused node
+    winograd_node(C, A, B, levels, clear, ws, s);
+    return;
+  }
+  TopHooks &hk = *hooks;
   if (levels == 0) {
     for (int q = 0; q < 4; ++q) { hk.need_a(q); hk.need_b(q); if (!clear) hk.need_c(q); }
     if (clear) launch_zero(C, s);
