@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "dev.h"
+#include "staging.h"
 #include "workspace.h"
 
 namespace m4b {
@@ -43,6 +44,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // PCIe transfers of the host path, overlapped with `stream`
   Workspace    ws;
+  Stager       stager;                  // pinned ring for pageable host matrices
   std::vector<word> host_tmp;
   char         last_path[64] = "none";
 };
@@ -100,23 +102,34 @@ mzd_t *alloc_result(rci_t r, rci_t c) {
 }  // namespace
 
 // ---- transfers (shared with multi.cu) ------------------------------------------------------
-void upload(DView dst, mzd_t const *src, cudaStream_t s) {
+constexpr size_t kStageThreshold = 4u << 20;   // below this the driver's own pageable path is as fast
+
+void upload(DView dst, mzd_t const *src, cudaStream_t s, Stager *st) {
   if (src->nrows == 0 || src->ncols == 0) return;
-  M4B_CUDA(cudaMemcpy2DAsync(dst.data, (size_t)dst.pitch * 8, src->data, (size_t)src->rowstride * 8,
-                             (size_t)src->width * 8, (size_t)src->nrows, cudaMemcpyHostToDevice, s));
+  size_t const width = (size_t)src->width * 8, rows = (size_t)src->nrows;
+  if (st && width * rows >= kStageThreshold && Stager::pageable(src->data))
+    st->upload2d(dst.data, (size_t)dst.pitch * 8, src->data, (size_t)src->rowstride * 8, width, rows, s);
+  else
+    M4B_CUDA(cudaMemcpy2DAsync(dst.data, (size_t)dst.pitch * 8, src->data, (size_t)src->rowstride * 8, width, rows,
+                               cudaMemcpyHostToDevice, s));
   if (src->ncols % 64) launch_mask_excess(DView{dst.data, dst.pitch, src->nrows, src->ncols}, s);
 }
 
 // Device rows -> host matrix, touching only bits (i < nrows, j < ncols) of the host matrix.
 // Whole words go straight into the host rows; a partial last word is staged in `tmp` and merged under
 // high_bitmask by download_finish() once the stream has been synchronised.
-void download_async(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp) {
+void download_async(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp, Stager *st = nullptr) {
   tmp.clear();
   if (dst->nrows == 0 || dst->ncols == 0) return;
   int64_t const full = dst->ncols / 64;   // whole words per row
-  if (full)
-    M4B_CUDA(cudaMemcpy2DAsync(dst->data, (size_t)dst->rowstride * 8, src.data, (size_t)src.pitch * 8,
-                               (size_t)full * 8, (size_t)dst->nrows, cudaMemcpyDeviceToHost, s));
+  if (full) {
+    size_t const width = (size_t)full * 8, rows = (size_t)dst->nrows;
+    if (st && width * rows >= kStageThreshold && Stager::pageable(dst->data))
+      st->download2d(dst->data, (size_t)dst->rowstride * 8, src.data, (size_t)src.pitch * 8, width, rows, s);
+    else
+      M4B_CUDA(cudaMemcpy2DAsync(dst->data, (size_t)dst->rowstride * 8, src.data, (size_t)src.pitch * 8, width, rows,
+                                 cudaMemcpyDeviceToHost, s));
+  }
   if (dst->ncols % 64) {
     tmp.resize((size_t)dst->nrows);
     M4B_CUDA(cudaMemcpy2DAsync(tmp.data(), 8, src.data + full, (size_t)src.pitch * 8, 8, (size_t)dst->nrows,
@@ -134,8 +147,8 @@ void download_finish(mzd_t *dst, std::vector<word> const &tmp) {
   }
 }
 
-void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp) {
-  download_async(dst, src, s, tmp);
+void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp, Stager *st) {
+  download_async(dst, src, s, tmp, st);
   if (!tmp.empty()) {
     M4B_CUDA(cudaStreamSynchronize(s));
     download_finish(dst, tmp);
@@ -205,7 +218,7 @@ struct HostOverlap : TopHooks {
     int r0, c0, r1, c1;
     quad(V, q, r0, c0, r1, c1);
     mzd_t W = host_window(M, r0, c0, r1, c1);
-    if (W.nrows > 0 && W.ncols > 0) upload(V.sub(r0, c0, r0 + W.nrows, c0 + W.ncols), &W, c.copy_stream);
+    if (W.nrows > 0 && W.ncols > 0) upload(V.sub(r0, c0, r0 + W.nrows, c0 + W.ncols), &W, c.copy_stream, &c.stager);
     cudaEvent_t e = event();
     M4B_CUDA(cudaEventRecord(e, c.copy_stream));
     M4B_CUDA(cudaStreamWaitEvent(c.stream, e, 0));
@@ -230,7 +243,7 @@ struct HostOverlap : TopHooks {
       cwin[q] = host_window(C, r0, c0, r1, c1);
       M4B_CUDA(cudaStreamWaitEvent(c.copy_stream, ready[q], 0));
       if (cwin[q].nrows > 0 && cwin[q].ncols > 0)
-        download_async(&cwin[q], dC.sub(r0, c0, r0 + cwin[q].nrows, c0 + cwin[q].ncols), c.copy_stream, tails[q]);
+        download_async(&cwin[q], dC.sub(r0, c0, r0 + cwin[q].nrows, c0 + cwin[q].ncols), c.copy_stream, tails[q], &c.stager);
     }
     M4B_CUDA(cudaStreamSynchronize(c.copy_stream));
     M4B_CUDA(cudaStreamSynchronize(c.stream));
@@ -267,11 +280,11 @@ void host_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool cle
     ov.finish();
     M4B_CUDA(cudaEventDestroy(zeroed));
   } else {
-    upload(dA, A, s);
-    upload(dB, B, s);
-    if (!clear) upload(dC, C, s);
+    upload(dA, A, s, &c.stager);
+    upload(dB, B, s, &c.stager);
+    if (!clear) upload(dC, C, s, &c.stager);
     strassen_mul(dC, dA, dB, levels, clear, c.ws, s);
-    download(C, dC, s, c.host_tmp);
+    download(C, dC, s, c.host_tmp, &c.stager);
     M4B_CUDA(cudaStreamSynchronize(s));
   }
   c.ws.release(0);
@@ -431,6 +444,7 @@ void m4ri_b200_release(void) {
   if (!g.ready) return;
   cudaStreamSynchronize(g.stream);
   g.ws.destroy();
+  g.stager.release();
 }
 
 char const *m4ri_b200_last_path(void) { return g.last_path; }
@@ -504,14 +518,14 @@ void m4ri_b200_dmat_free(m4ri_b200_dmat *M) {
 
 void m4ri_b200_upload(m4ri_b200_dmat *dst, mzd_t const *src, void *stream) {
   if (dst->nrows != src->nrows || dst->ncols != src->ncols) die("m4ri_b200_upload: dimension mismatch\n");
-  upload(as_view(dst), src, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+  upload(as_view(dst), src, stream ? static_cast<cudaStream_t>(stream) : ctx().stream, &ctx().stager);
   if (!stream) M4B_CUDA(cudaStreamSynchronize(ctx().stream));
 }
 
 void m4ri_b200_download(mzd_t *dst, m4ri_b200_dmat const *src, void *stream) {
   if (dst->nrows != src->nrows || dst->ncols != src->ncols) die("m4ri_b200_download: dimension mismatch\n");
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
-  download(dst, as_view(src), s, ctx().host_tmp);
+  download(dst, as_view(src), s, ctx().host_tmp, &ctx().stager);
   M4B_CUDA(cudaStreamSynchronize(s));
 }
 

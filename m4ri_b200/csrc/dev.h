@@ -59,8 +59,9 @@ void launch_winograd_pre_b(DView const b[4], DView const t_out[4], cudaStream_t 
 void launch_winograd_post(DView const p[7], DView const c[4], bool accumulate, cudaStream_t stream);
 
 // ---- host <-> device transfers (capi.cu) ----------------------------------------------
-void upload(DView dst, mzd_t const *src, cudaStream_t s);                 // excess bits cleared on device
-void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp);   // only valid bits of dst change
+class Stager;   // staging.h: pinned-ring transfers for pageable host memory (optional)
+void upload(DView dst, mzd_t const *src, cudaStream_t s, Stager *st = nullptr);   // excess bits cleared on device
+void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp, Stager *st = nullptr);   // only valid bits of dst change
 void zero_async(DView v, cudaStream_t s);
 
 // ---- multi-GPU row-block product (multi.cu) --------------------------------------------

@@ -39,15 +39,20 @@ def run(m, l, n, cutoff, iters=5):
     for _ in range(2):
         go()
     torch.cuda.synchronize()
+    import ctypes
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.m4ri_b200_profile_begin()
     e0.record()
     for _ in range(iters):
         go()
     e1.record()
     torch.cuda.synchronize()
+    lms, lops = ctypes.c_double(0), ctypes.c_double(0)
+    nl = lib.m4ri_b200_profile_end(ctypes.byref(lms), ctypes.byref(lops))
     ms = e0.elapsed_time(e1) / iters
     print(f"{m}x{l}x{n} cutoff={cutoff} path={lib.m4ri_b200_last_path().decode()} "
-          f"{ms:.3f} ms {2.0*m*l*n/ms/1e9:.1f} Tbitops/s", flush=True)
+          f"{ms:.3f} ms {2.0*m*l*n/ms/1e9:.1f} Tbitops/s | leaf launches/iter {nl//iters} "
+          f"leaf ms/iter {lms.value/iters:.3f} leaf rate {lops.value/lms.value/1e9:.1f} T/s", flush=True)
 
 
 if __name__ == "__main__":
