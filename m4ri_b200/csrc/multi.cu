@@ -16,9 +16,11 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <memory>
 #include <thread>
 
 #include "dev.h"
+#include "staging.h"
 #include "workspace.h"
 
 namespace m4b {
@@ -63,21 +65,23 @@ struct Dev {
   int          id = 0;
   cudaStream_t stream = nullptr;
   Workspace    ws;
+  Stager       stager;        // pinned ring for pageable host rows (one per GPU: the uploads run concurrently)
   std::vector<word> tmp;
 };
-std::vector<Dev>        devs;
+std::vector<std::unique_ptr<Dev>> devs;   // Dev holds a Stager (threads, mutex): not movable
+Dev &dev(int g) { return *devs[g]; }
 std::vector<ncclComm_t> comms;
 
 void setup(int G) {
   if ((int)devs.size() == G) return;
   multi_release();
   load_nccl();
-  devs.resize(G);
+  for (int g = 0; g < G; ++g) devs.emplace_back(new Dev);
   std::vector<int> ids(G);
   for (int g = 0; g < G; ++g) {
-    devs[g].id = ids[g] = g;
+    dev(g).id = ids[g] = g;
     M4B_CUDA(cudaSetDevice(g));
-    M4B_CUDA(cudaStreamCreateWithFlags(&devs[g].stream, cudaStreamNonBlocking));
+    M4B_CUDA(cudaStreamCreateWithFlags(&dev(g).stream, cudaStreamNonBlocking));
   }
   comms.resize(G);
   M4B_NCCL(nccl.CommInitAll(comms.data(), G, ids.data()));
@@ -89,7 +93,7 @@ int64_t gcd64(int64_t a, int64_t b) { return b ? gcd64(b, a % b) : a; }
 template <class F>
 void per_device(int G, F &&f) {
   std::vector<std::thread> th;
-  for (int g = 0; g < G; ++g) th.emplace_back([&, g] { M4B_CUDA(cudaSetDevice(devs[g].id)); f(g); });
+  for (int g = 0; g < G; ++g) th.emplace_back([&, g] { M4B_CUDA(cudaSetDevice(dev(g).id)); f(g); });
   for (auto &t : th) t.join();
 }
 
@@ -109,10 +113,11 @@ void multi_release() {
     if (nccl.CommDestroy) nccl.CommDestroy(c);
   comms.clear();
   for (auto &d : devs) {
-    cudaSetDevice(d.id);
-    cudaStreamSynchronize(d.stream);
-    d.ws.destroy();
-    cudaStreamDestroy(d.stream);
+    cudaSetDevice(d->id);
+    cudaStreamSynchronize(d->stream);
+    d->ws.destroy();
+    d->stager.release();
+    cudaStreamDestroy(d->stream);
   }
   devs.clear();
 }
@@ -141,7 +146,7 @@ void multi_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool cl
 
   std::vector<DView> dA(G), dB(G), dC(G);
   per_device(G, [&](int g) {
-    Dev &d = devs[g];
+    Dev &d = dev(g);
     d.ws.reserve(Workspace::bytes_for(mpb, (int)lp) + Workspace::bytes_for((int)lp, np) + Workspace::bytes_for(mpb, np) +
                  strassen_workspace_bytes(mpb, (int)lp, np, levels));
     dA[g] = d.ws.alloc(mpb, (int)lp);
@@ -152,17 +157,17 @@ void multi_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool cl
     int const r0 = g * rb < m ? g * rb : m, r1 = (g + 1) * rb < m ? (g + 1) * rb : m;
     if (r1 > r0) {
       mzd_t Ablk = row_window(A, r0, r1);
-      upload(dA[g].sub(0, 0, r1 - r0, (int)lp), &Ablk, d.stream);
+      upload(dA[g].sub(0, 0, r1 - r0, (int)lp), &Ablk, d.stream, &d.stager);
       if (!clear) {
         zero_async(dC[g], d.stream);
         mzd_t Cblk = row_window(C, r0, r1);
-        upload(dC[g].sub(0, 0, r1 - r0, np), &Cblk, d.stream);
+        upload(dC[g].sub(0, 0, r1 - r0, np), &Cblk, d.stream, &d.stager);
       }
     }
     int const s0 = g * lb < l ? g * lb : l, s1 = (g + 1) * lb < l ? (g + 1) * lb : l;
     if (s1 > s0) {
       mzd_t Bsl = row_window(B, s0, s1);
-      upload(dB[g].sub(g * lb, 0, g * lb + (s1 - s0), np), &Bsl, d.stream);
+      upload(dB[g].sub(g * lb, 0, g * lb + (s1 - s0), np), &Bsl, d.stream, &d.stager);
     }
   });
 
@@ -171,22 +176,22 @@ void multi_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool cl
   M4B_NCCL(nccl.GroupStart());
   for (int g = 0; g < G; ++g)
     M4B_NCCL(nccl.AllGather(dB[g].data + (size_t)g * slice_words, dB[g].data, slice_words, ncclUint64, comms[g],
-                            devs[g].stream));
+                            dev(g).stream));
   M4B_NCCL(nccl.GroupEnd());
 
   for (int g = 0; g < G; ++g) {
     int const r0 = g * rb < m ? g * rb : m, r1 = (g + 1) * rb < m ? (g + 1) * rb : m;
     if (r1 <= r0) continue;
-    M4B_CUDA(cudaSetDevice(devs[g].id));
-    strassen_mul(dC[g], dA[g], dB[g], levels, clear, devs[g].ws, devs[g].stream);
+    M4B_CUDA(cudaSetDevice(dev(g).id));
+    strassen_mul(dC[g], dA[g], dB[g], levels, clear, dev(g).ws, dev(g).stream);
   }
 
   per_device(G, [&](int g) {
-    Dev &d = devs[g];
+    Dev &d = dev(g);
     int const r0 = g * rb < m ? g * rb : m, r1 = (g + 1) * rb < m ? (g + 1) * rb : m;
     if (r1 > r0) {
       mzd_t Cblk = row_window(C, r0, r1);
-      download(&Cblk, dC[g].sub(0, 0, r1 - r0, np), d.stream, d.tmp);
+      download(&Cblk, dC[g].sub(0, 0, r1 - r0, np), d.stream, d.tmp, &d.stager);
     }
     M4B_CUDA(cudaStreamSynchronize(d.stream));
     d.ws.release(0);
