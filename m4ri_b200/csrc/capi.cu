@@ -298,6 +298,32 @@ mzd_t *checked(char const *who, mzd_t *C, mzd_t const *A, mzd_t const *B) {
   return C;
 }
 
+// Host path of the left triangular solves: T (m x m) and B (m x n) up, recursion on the device, X down
+// into B (only its valid bits).
+void host_trsm_left(mzd_t const *T, mzd_t *B, int cutoff, bool upper) {
+  Ctx &c = ctx();
+  int const m = B->nrows, n = B->ncols;
+  if (m == 0 || n == 0) return;
+  ++g_products;
+  snprintf(c.last_path, sizeof c.last_path, upper ? "trsm_upper_left" : "trsm_lower_left");
+  c.ws.reserve(Workspace::bytes_for(m, m) + Workspace::bytes_for(m, n) + trsm_workspace_bytes(m, n, cutoff));
+  cudaStream_t s = c.stream;
+  DView dT = c.ws.alloc(m, m), dB = c.ws.alloc(m, n);
+  zero_async(dT, s);
+  zero_async(dB, s);
+  upload(dT, T, s, &c.stager);
+  upload(dB, B, s, &c.stager);
+  trsm_left(dT, dB, upper, cutoff, c.ws, s);
+  download(B, dB, s, c.host_tmp, &c.stager);
+  M4B_CUDA(cudaStreamSynchronize(s));
+  c.ws.release(0);
+}
+
+void check_trsm(char const *who, mzd_t const *T, mzd_t const *B) {   // m4ri/triangular.c:394-401, 457-464
+  if (T->ncols != B->nrows) die("%s: triangular ncols (%d) need to match B nrows (%d).\n", who, T->ncols, B->nrows);
+  if (T->nrows != T->ncols) die("%s: triangular matrix must be square and is found to be (%d) x (%d).\n", who, T->nrows, T->ncols);
+}
+
 DView as_view(m4ri_b200_dmat const *M) { return DView{M->data, M->pitch, M->nrows, M->ncols}; }
 
 void device_product(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int levels, bool clear,
@@ -393,6 +419,22 @@ mzd_t *mzd_addmul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k) {
   if (C != NULL && (C->ncols == 0 || C->nrows == 0)) return C;
   C = checked("mzd_addmul_m4rm", C, A, B);
   return _mzd_mul_m4rm(C, A, B, k, 0);
+}
+
+// ---- widened rows: triangular solves, left variants (m4ri/triangular.h:115,127,142,153) ----
+void mzd_trsm_lower_left(mzd_t const *L, mzd_t *B, int const cutoff) {
+  check_trsm("mzd_trsm_lower_left", L, B);
+  host_trsm_left(L, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "mzd_trsm_lower_left"), false);
+}
+void _mzd_trsm_lower_left(mzd_t const *L, mzd_t *B, int const cutoff) {
+  host_trsm_left(L, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "_mzd_trsm_lower_left"), false);
+}
+void mzd_trsm_upper_left(mzd_t const *U, mzd_t *B, int const cutoff) {
+  check_trsm("mzd_trsm_upper_left", U, B);
+  host_trsm_left(U, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "mzd_trsm_upper_left"), true);
+}
+void _mzd_trsm_upper_left(mzd_t const *U, mzd_t *B, int const cutoff) {
+  host_trsm_left(U, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "_mzd_trsm_upper_left"), true);
 }
 
 // Row-blocks of C over the GPUs chosen with m4ri_b200_set_num_devices (multi.cu); one GPU: same as mzd_mul.
@@ -549,6 +591,15 @@ void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200
   if (levels < 0 || levels > 12) die("m4ri_b200_dmul_levels: levels must be in 0..12\n");
   while (levels > 0 && ((A->nrows >> levels) < 1 || (A->ncols >> levels) < 128 || (B->ncols >> levels) < 128)) --levels;
   device_product(C, A, B, levels, clear != 0, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+}
+
+void m4ri_b200_dtrsm_left(m4ri_b200_dmat const *T, m4ri_b200_dmat *B, int upper, int cutoff, void *stream) {
+  if (T->nrows != T->ncols || T->ncols != B->nrows) die("m4ri_b200_dtrsm_left: dimension mismatch\n");
+  Ctx &c = ctx();
+  cutoff = norm_cutoff(cutoff, "m4ri_b200_dtrsm_left");
+  c.ws.reserve(trsm_workspace_bytes(B->nrows, B->ncols, cutoff));
+  snprintf(c.last_path, sizeof c.last_path, upper ? "trsm_upper_left" : "trsm_lower_left");
+  trsm_left(as_view(T), as_view(B), upper != 0, cutoff, c.ws, stream ? static_cast<cudaStream_t>(stream) : c.stream);
 }
 
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {

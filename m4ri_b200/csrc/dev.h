@@ -87,4 +87,9 @@ struct TopHooks {
 void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s,
                   TopHooks *hooks = nullptr);
 
+// ---- triangular solve, left variants (trsm.cu) -----------------------------------------------
+// T: m x m (strict triangle read, unit diagonal implied), B: m x n, X overwrites B.
+void   trsm_left(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s);
+size_t trsm_workspace_bytes(int m, int n, int cutoff);
+
 }  // namespace m4b

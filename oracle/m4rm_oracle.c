@@ -439,3 +439,28 @@ orc_mzd *orc_addmul(orc_mzd *C, orc_mzd const *A, orc_mzd const *B, int cutoff) 
   addmul_even(C, A, B, cutoff);
   return C;
 }
+
+/* ---- triangular solves with matrices, left variants (first "next" row) ----------
+ * m4ri/triangular.c:406-455 (lower left) and :467-516 (upper left): L X = B resp. U X = B, X
+ * overwrites B.  The triangular matrix is read with an implied unit diagonal and only its strict
+ * triangle is used (triangular.c:413-425).  The reference recurses with mzd_addmul and a
+ * "russian" base case; the result is the unique solution, restated here as plain substitution. */
+
+static void xor_row_valid(orc_mzd *B, orc_rci dst, orc_rci src) {
+  orc_word *d = rowp(B, dst);
+  orc_word const *s = rowp(B, src);
+  for (orc_wi j = 0; j + 1 < B->width; ++j) d[j] ^= s[j];
+  if (B->width) d[B->width - 1] ^= s[B->width - 1] & B->high_bitmask;
+}
+
+void orc_trsm_lower_left(orc_mzd const *L, orc_mzd *B) {
+  for (orc_rci i = 1; i < B->nrows; ++i)
+    for (orc_rci k = 0; k < i; ++k)
+      if ((rowp(L, i)[k / RADIX] >> (k % RADIX)) & 1) xor_row_valid(B, i, k);
+}
+
+void orc_trsm_upper_left(orc_mzd const *U, orc_mzd *B) {
+  for (orc_rci i = B->nrows - 2; i >= 0; --i)
+    for (orc_rci k = i + 1; k < B->nrows; ++k)
+      if ((rowp(U, i)[k / RADIX] >> (k % RADIX)) & 1) xor_row_valid(B, i, k);
+}

@@ -57,6 +57,10 @@ orc_mzd *orc_mul_m4rm(orc_mzd *C, orc_mzd const *A, orc_mzd const *B, int k, int
 orc_mzd *orc_mul(orc_mzd *C, orc_mzd const *A, orc_mzd const *B, int cutoff);
 orc_mzd *orc_addmul(orc_mzd *C, orc_mzd const *A, orc_mzd const *B, int cutoff);
 
+/* L X = B / U X = B, X overwrites B; unit diagonal implied (m4ri/triangular.c:406-516) */
+void     orc_trsm_lower_left(orc_mzd const *L, orc_mzd *B);
+void     orc_trsm_upper_left(orc_mzd const *U, orc_mzd *B);
+
 #ifdef __cplusplus
 }
 #endif

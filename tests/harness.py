@@ -52,6 +52,8 @@ def oracle():
         lib.orc_mul_m4rm.argtypes, lib.orc_mul_m4rm.restype = [MzdP, MzdP, MzdP, c_int, c_int], MzdP
         lib.orc_mul.argtypes, lib.orc_mul.restype = [MzdP, MzdP, MzdP, c_int], MzdP
         lib.orc_addmul.argtypes, lib.orc_addmul.restype = [MzdP, MzdP, MzdP, c_int], MzdP
+        lib.orc_trsm_lower_left.argtypes = [MzdP, MzdP]
+        lib.orc_trsm_upper_left.argtypes = [MzdP, MzdP]
         _oracle = lib
     return _oracle
 
@@ -76,6 +78,9 @@ def _declare_ref(lib):
     lib.m4ri_build_code.argtypes = [POINTER(c_int), POINTER(c_int), c_int]
     lib.mzd_make_table.argtypes = [MzdP, c_int, c_int, c_int, MzdP, POINTER(c_int)]
     lib.m4ri_random_word.restype = c_uint64
+    for name in ("mzd_trsm_lower_left", "mzd_trsm_upper_left", "mzd_trsm_lower_right", "mzd_trsm_upper_right"):
+        getattr(lib, name).argtypes = [MzdP, MzdP, c_int]
+        getattr(lib, name).restype = None
     if hasattr(lib, "mzd_mul_mp"):
         lib.mzd_mul_mp.argtypes, lib.mzd_mul_mp.restype = three, MzdP
         lib.mzd_addmul_mp.argtypes, lib.mzd_addmul_mp.restype = three, MzdP
