@@ -9,9 +9,9 @@
 // — but the operands stay in HBM for the whole solve, the update is the Strassen/M4RM product of this
 // library (accumulate form) on sub-views, and the recursion splits on 128-column boundaries down to a
 // 128-row base case.  The reference's base cases (64-row substitution and the "russian" table variant,
-// triangular_russian.c:50-168) are replaced by one kernel: columns of B are independent, so each thread
-// owns one 32-bit column word of all <= 128 rows (staged in shared memory, one bank per thread) and
-// substitutes along the set bits of the triangular block.
+// triangular_russian.c:50-168) are replaced by products as well: all 128 x 128 diagonal blocks are
+// inverted up front in one small launch (they do not depend on B), and a base step is
+// X_block = inv(T_block) * B_block on the M4RM leaf, which is parallel over all columns of B.
 #include "dev.h"
 #include "workspace.h"
 
@@ -19,70 +19,38 @@ namespace m4b {
 namespace {
 
 constexpr int kBaseRows = 128;
-constexpr int kBaseThreads = 64;
 
-// T: rows [0, m) x cols [0, m) of the diagonal block (bit j of row i at t[i*tpitch32 + j/32]);
-// B: m rows of nw32 32-bit words.
+// Inverse of every 128 x 128 diagonal block of T in ONE launch (one warp per block; the blocks are
+// independent of B and of each other).  Row i of the inverse is e_i plus the XOR of the already
+// inverted rows k selected by the strict triangle of T's row i; the 32 lanes split the k range and
+// combine with shuffles.  inv: m rows x 128 bits (pitch 2 words), block b in rows [128 b, 128 b + 128).
 template <bool UPPER>
-__global__ void __launch_bounds__(kBaseThreads) trsm_base_kernel(uint32_t const *__restrict__ t, long long tpitch32,
-                                                                 uint32_t *__restrict__ b, long long bpitch32, int m,
-                                                                 int nw32) {
-  __shared__ uint32_t tri[kBaseRows][4];
-  __shared__ uint32_t x[kBaseRows][kBaseThreads];
-  int const tid = threadIdx.x;
-  int const w = blockIdx.x * kBaseThreads + tid;
-  for (int i = tid; i < kBaseRows * 4; i += kBaseThreads) {
-    int const r = i >> 2, c = i & 3;
-    tri[r][c] = (r < m && c * 32 < m) ? t[r * tpitch32 + c] : 0u;
-  }
-  if (w < nw32)
-    for (int i = 0; i < m; ++i) x[i][tid] = b[i * bpitch32 + w];
-  __syncthreads();
-  if (w >= nw32) return;
-  if (!UPPER) {
-    for (int i = 1; i < m; ++i) {            // X_i = B_i + sum_{k < i, L[i][k]} X_k
-      uint32_t acc = x[i][tid];
-      for (int c = 0; c * 32 < i; ++c) {
-        uint32_t bits = tri[i][c];
-        if (i - c * 32 < 32) bits &= (1u << (i - c * 32)) - 1u;     // strictly below the diagonal
-        while (bits) {
-          int const k = c * 32 + __ffs(bits) - 1;
-          bits &= bits - 1;
-          acc ^= x[k][tid];
-        }
+__global__ void __launch_bounds__(32) tri_inv128_kernel(uint32_t const *__restrict__ t, long long tpitch32,
+                                                        uint32_t *__restrict__ inv, int m) {
+  __shared__ uint32_t rows[kBaseRows][4];
+  int const blk = blockIdx.x, lane = threadIdx.x;
+  int const r0 = blk * kBaseRows;
+  int const r = m - r0 < kBaseRows ? m - r0 : kBaseRows;       // rows in this block
+  for (int step = 0; step < r; ++step) {
+    int const i = UPPER ? r - 1 - step : step;
+    uint32_t const *trow = t + (long long)(r0 + i) * tpitch32 + blk * 4;
+    uint32_t acc[4] = {0, 0, 0, 0};
+    for (int k = lane; k < r; k += 32) {
+      bool const in_triangle = UPPER ? k > i : k < i;
+      if (in_triangle && ((trow[k >> 5] >> (k & 31)) & 1u)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] ^= rows[k][c];
       }
-      x[i][tid] = acc;
     }
-  } else {
-    for (int i = m - 2; i >= 0; --i) {       // X_i = B_i + sum_{k > i, U[i][k]} X_k
-      uint32_t acc = x[i][tid];
-      for (int c = (i + 1) >> 5; c * 32 < m; ++c) {
-        uint32_t bits = tri[i][c];
-        if (c * 32 <= i) bits &= ~((2u << (i - c * 32)) - 1u);      // strictly above the diagonal
-        if (m - c * 32 < 32) bits &= (1u << (m - c * 32)) - 1u;     // columns >= m do not exist
-        while (bits) {
-          int const k = c * 32 + __ffs(bits) - 1;
-          bits &= bits - 1;
-          acc ^= x[k][tid];
-        }
-      }
-      x[i][tid] = acc;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int off = 16; off; off >>= 1) acc[c] ^= __shfl_xor_sync(0xffffffffu, acc[c], off);
     }
+    if (lane < 4) rows[i][lane] = acc[lane] ^ ((i >> 5) == lane ? 1u << (i & 31) : 0u);
+    __syncwarp();
   }
-  for (int i = 0; i < m; ++i) b[i * bpitch32 + w] = x[i][tid];
-}
-
-void launch_base(DView T, DView B, bool upper, cudaStream_t s) {
-  int const nw32 = ((B.ncols + 127) / 128) * 4;
-  unsigned const grid = (nw32 + kBaseThreads - 1) / kBaseThreads;
-  auto const *t = reinterpret_cast<uint32_t const *>(T.data);
-  auto *b = reinterpret_cast<uint32_t *>(B.data);
-  if (upper)
-    trsm_base_kernel<true><<<grid, kBaseThreads, 0, s>>>(t, T.pitch * 2, b, B.pitch * 2, B.nrows, nw32);
-  else
-    trsm_base_kernel<false><<<grid, kBaseThreads, 0, s>>>(t, T.pitch * 2, b, B.pitch * 2, B.nrows, nw32);
-  M4B_CUDA(cudaGetLastError());
-  ++g_kernel_launches;
+  for (int i = lane; i < r * 4; i += 32) inv[(long long)(r0 + (i >> 2)) * 4 + (i & 3)] = rows[i >> 2][i & 3];
 }
 
 // C ^= A*B on views with the deepest Strassen recursion the views' alignment allows
@@ -97,28 +65,57 @@ void addmul_views(DView C, DView A, DView B, int cutoff, Workspace &ws, cudaStre
 size_t trsm_workspace_bytes(int m, int n, int cutoff) {
   // every update product is at most m x m x n; its Strassen temporaries bound all the smaller ones
   int const mp = (m + 127) / 128 * 128, np = (n + 127) / 128 * 128;
-  return strassen_workspace_bytes(mp, mp, np, strassen_levels(m, m, n, cutoff));
+  return strassen_workspace_bytes(mp, mp, np, strassen_levels(m, m, n, cutoff)) + Workspace::bytes_for(m, kBaseRows) +
+         Workspace::bytes_for(kBaseRows, n);
 }
 
-void trsm_left(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s) {
+namespace {
+
+// recursion below the top: Tinv holds the inverted diagonal blocks of the WHOLE matrix, row0 = first
+// row of this sub-problem inside it
+void trsm_rec(DView T, DView B, DView Tinv, int row0, bool upper, int cutoff, Workspace &ws, cudaStream_t s) {
   int const m = B.nrows, n = B.ncols;
-  if (m <= 0 || n <= 0) return;
   if (m <= kBaseRows) {
-    launch_base(T, B, upper, s);
+    // X = inv(T_block) * B_block: one 128-row product of the M4RM leaf (full-chip parallel over the
+    // columns of B), through a temporary because the kernel cannot read and accumulate in place
+    size_t const mark = ws.mark();
+    DView X = ws.alloc(m, n);
+    launch_zero(X, s);
+    launch_m4rm(X, Tinv.sub(row0, 0, row0 + m, m), B, s);
+    launch_copy(B, X, s);
+    ws.release(mark);
     return;
   }
   int const m1 = ((m + 127) / 128 / 2) * 128;          // multiple of 128, 0 < m1 < m
   DView const T00 = T.sub(0, 0, m1, m1), T11 = T.sub(m1, m1, m, m);
   DView const B0 = B.sub(0, 0, m1, n), B1 = B.sub(m1, 0, m, n);
   if (!upper) {
-    trsm_left(T00, B0, false, cutoff, ws, s);
+    trsm_rec(T00, B0, Tinv, row0, false, cutoff, ws, s);
     addmul_views(B1, T.sub(m1, 0, m, m1), B0, cutoff, ws, s);
-    trsm_left(T11, B1, false, cutoff, ws, s);
+    trsm_rec(T11, B1, Tinv, row0 + m1, false, cutoff, ws, s);
   } else {
-    trsm_left(T11, B1, true, cutoff, ws, s);
+    trsm_rec(T11, B1, Tinv, row0 + m1, true, cutoff, ws, s);
     addmul_views(B0, T.sub(0, m1, m1, m), B1, cutoff, ws, s);
-    trsm_left(T00, B0, true, cutoff, ws, s);
+    trsm_rec(T00, B0, Tinv, row0, true, cutoff, ws, s);
   }
+}
+
+}  // namespace
+
+void trsm_left(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s) {
+  int const m = B.nrows, n = B.ncols;
+  if (m <= 0 || n <= 0) return;
+  size_t const mark = ws.mark();
+  DView Tinv = ws.alloc(m, kBaseRows);
+  unsigned const blocks = (m + kBaseRows - 1) / kBaseRows;
+  auto const *t = reinterpret_cast<uint32_t const *>(T.data);
+  auto *inv = reinterpret_cast<uint32_t *>(Tinv.data);
+  if (upper) tri_inv128_kernel<true><<<blocks, 32, 0, s>>>(t, T.pitch * 2, inv, m);
+  else       tri_inv128_kernel<false><<<blocks, 32, 0, s>>>(t, T.pitch * 2, inv, m);
+  M4B_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+  trsm_rec(T, B, Tinv, 0, upper, cutoff, ws, s);
+  ws.release(mark);
 }
 
 }  // namespace m4b
