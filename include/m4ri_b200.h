@@ -70,13 +70,18 @@ mzd_t *_mzd_mul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k, int clear)
 mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
 mzd_t *mzd_addmul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
 
-/* Widened rows (callers of the multiplication path): L X = B and U X = B with matrices, X overwrites
- * B, unit diagonal implied, only the strict triangle is read.  m4ri/triangular.h:115,127,142,153;
- * triangular.c:394-516.  (The right variants mzd_trsm_*_right stay with libm4ri.) */
+/* Widened rows (callers of the multiplication path): triangular solves with matrices, X overwrites B,
+ * unit diagonal implied, only the strict triangle of the triangular operand is read.
+ *   left:  L X = B, U X = B   m4ri/triangular.h:115,127,142,153; triangular.c:394-516
+ *   right: X L = B, X U = B   m4ri/triangular.h:50,64,82,100;   triangular.c:29-148, 300-392 */
 void mzd_trsm_lower_left(mzd_t const *L, mzd_t *B, const int cutoff);
 void _mzd_trsm_lower_left(mzd_t const *L, mzd_t *B, const int cutoff);
 void mzd_trsm_upper_left(mzd_t const *U, mzd_t *B, const int cutoff);
 void _mzd_trsm_upper_left(mzd_t const *U, mzd_t *B, const int cutoff);
+void mzd_trsm_lower_right(mzd_t const *L, mzd_t *B, const int cutoff);
+void _mzd_trsm_lower_right(mzd_t const *L, mzd_t *B, const int cutoff);
+void mzd_trsm_upper_right(mzd_t const *U, mzd_t *B, const int cutoff);
+void _mzd_trsm_upper_right(mzd_t const *U, mzd_t *B, const int cutoff);
 
 /* ---- Part 2: extension API --------------------------------------------------------- */
 
@@ -133,8 +138,9 @@ void m4ri_b200_dmul_m4rm(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_d
 void m4ri_b200_dmul(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int cutoff, int clear, void *stream);
 /* as dmul with the Strassen depth given explicitly (0 = leaf only); for cutoff sweeps. */
 void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int levels, int clear, void *stream);
-/* T X = B on device matrices (T lower triangular, or upper if upper != 0), X overwrites B. */
-void m4ri_b200_dtrsm_left(m4ri_b200_dmat const *T, m4ri_b200_dmat *B, int upper, int cutoff, void *stream);
+/* T X = B (left != 0) or X T = B (left == 0) on device matrices, T lower triangular or upper if
+ * upper != 0; X overwrites B. */
+void m4ri_b200_dtrsm(m4ri_b200_dmat const *T, m4ri_b200_dmat *B, int upper, int left, int cutoff, void *stream);
 /* C = A ^ B on device matrices (the device form of _mzd_add, m4ri/mzd.c:1471-1583). */
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream);
 

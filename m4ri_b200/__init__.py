@@ -65,10 +65,11 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = three, MzdP
     lib._mzd_mul_m4rm.argtypes, lib._mzd_mul_m4rm.restype = [MzdP, MzdP, MzdP, c_int, c_int], MzdP
-    for name in ("mzd_trsm_lower_left", "_mzd_trsm_lower_left", "mzd_trsm_upper_left", "_mzd_trsm_upper_left"):
-        fn = getattr(lib, name)
-        fn.argtypes, fn.restype = [MzdP, MzdP, c_int], None
-    lib.m4ri_b200_dtrsm_left.argtypes = [DMatP, DMatP, c_int, c_int, c_void_p]
+    for side in ("lower_left", "upper_left", "lower_right", "upper_right"):
+        for prefix in ("mzd_trsm_", "_mzd_trsm_"):
+            fn = getattr(lib, prefix + side)
+            fn.argtypes, fn.restype = [MzdP, MzdP, c_int], None
+    lib.m4ri_b200_dtrsm.argtypes = [DMatP, DMatP, c_int, c_int, c_int, c_void_p]
     lib.m4ri_b200_version.restype = c_int
     lib.m4ri_b200_device_count.restype = c_int
     lib.m4ri_b200_set_device.argtypes = [c_int]
@@ -180,3 +181,13 @@ def mzd_trsm_lower_left(L, B, cutoff: int = 0) -> None:
 def mzd_trsm_upper_left(U, B, cutoff: int = 0) -> None:
     """U X = B, X overwrites B (m4ri/triangular.c:457-516)."""
     load_library().mzd_trsm_upper_left(U, B, cutoff)
+
+
+def mzd_trsm_lower_right(L, B, cutoff: int = 0) -> None:
+    """X L = B, X overwrites B (m4ri/triangular.c:300-392)."""
+    load_library().mzd_trsm_lower_right(L, B, cutoff)
+
+
+def mzd_trsm_upper_right(U, B, cutoff: int = 0) -> None:
+    """X U = B, X overwrites B (m4ri/triangular.c:29-148)."""
+    load_library().mzd_trsm_upper_right(U, B, cutoff)

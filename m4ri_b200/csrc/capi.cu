@@ -298,29 +298,31 @@ mzd_t *checked(char const *who, mzd_t *C, mzd_t const *A, mzd_t const *B) {
   return C;
 }
 
-// Host path of the left triangular solves: T (m x m) and B (m x n) up, recursion on the device, X down
-// into B (only its valid bits).
-void host_trsm_left(mzd_t const *T, mzd_t *B, int cutoff, bool upper) {
+// Host path of the triangular solves: T (t x t) and B (m x n) up, recursion on the device, X down into
+// B (only its valid bits).  left: T X = B (t == m), right: X T = B (t == n).
+void host_trsm(mzd_t const *T, mzd_t *B, int cutoff, bool upper, bool left) {
   Ctx &c = ctx();
-  int const m = B->nrows, n = B->ncols;
+  int const m = B->nrows, n = B->ncols, t = T->nrows;
   if (m == 0 || n == 0) return;
   ++g_products;
-  snprintf(c.last_path, sizeof c.last_path, upper ? "trsm_upper_left" : "trsm_lower_left");
-  c.ws.reserve(Workspace::bytes_for(m, m) + Workspace::bytes_for(m, n) + trsm_workspace_bytes(m, n, cutoff));
+  snprintf(c.last_path, sizeof c.last_path, "trsm_%s_%s", upper ? "upper" : "lower", left ? "left" : "right");
+  c.ws.reserve(Workspace::bytes_for(t, t) + Workspace::bytes_for(m, n) + trsm_workspace_bytes(t, m, n, cutoff));
   cudaStream_t s = c.stream;
-  DView dT = c.ws.alloc(m, m), dB = c.ws.alloc(m, n);
+  DView dT = c.ws.alloc(t, t), dB = c.ws.alloc(m, n);
   zero_async(dT, s);
   zero_async(dB, s);
   upload(dT, T, s, &c.stager);
   upload(dB, B, s, &c.stager);
-  trsm_left(dT, dB, upper, cutoff, c.ws, s);
+  if (left) trsm_left(dT, dB, upper, cutoff, c.ws, s);
+  else      trsm_right(dT, dB, upper, cutoff, c.ws, s);
   download(B, dB, s, c.host_tmp, &c.stager);
   M4B_CUDA(cudaStreamSynchronize(s));
   c.ws.release(0);
 }
 
-void check_trsm(char const *who, mzd_t const *T, mzd_t const *B) {   // m4ri/triangular.c:394-401, 457-464
-  if (T->ncols != B->nrows) die("%s: triangular ncols (%d) need to match B nrows (%d).\n", who, T->ncols, B->nrows);
+void check_trsm(char const *who, mzd_t const *T, mzd_t const *B, bool left) {   // m4ri/triangular.c:29-36, 300-307, 394-401, 457-464
+  if (left && T->ncols != B->nrows) die("%s: triangular ncols (%d) need to match B nrows (%d).\n", who, T->ncols, B->nrows);
+  if (!left && T->nrows != B->ncols) die("%s: triangular nrows (%d) need to match B ncols (%d).\n", who, T->nrows, B->ncols);
   if (T->nrows != T->ncols) die("%s: triangular matrix must be square and is found to be (%d) x (%d).\n", who, T->nrows, T->ncols);
 }
 
@@ -422,20 +424,19 @@ mzd_t *mzd_addmul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k) {
 }
 
 // ---- widened rows: triangular solves, left variants (m4ri/triangular.h:115,127,142,153) ----
-void mzd_trsm_lower_left(mzd_t const *L, mzd_t *B, int const cutoff) {
-  check_trsm("mzd_trsm_lower_left", L, B);
-  host_trsm_left(L, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "mzd_trsm_lower_left"), false);
-}
-void _mzd_trsm_lower_left(mzd_t const *L, mzd_t *B, int const cutoff) {
-  host_trsm_left(L, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "_mzd_trsm_lower_left"), false);
-}
-void mzd_trsm_upper_left(mzd_t const *U, mzd_t *B, int const cutoff) {
-  check_trsm("mzd_trsm_upper_left", U, B);
-  host_trsm_left(U, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "mzd_trsm_upper_left"), true);
-}
-void _mzd_trsm_upper_left(mzd_t const *U, mzd_t *B, int const cutoff) {
-  host_trsm_left(U, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "_mzd_trsm_upper_left"), true);
-}
+#define M4B_TRSM_ENTRY(NAME, UPPER, LEFT)                                                           \
+  void mzd_##NAME(mzd_t const *T, mzd_t *B, int const cutoff) {                                     \
+    check_trsm("mzd_" #NAME, T, B, LEFT);                                                           \
+    host_trsm(T, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "mzd_" #NAME), UPPER, LEFT);               \
+  }                                                                                                 \
+  void _mzd_##NAME(mzd_t const *T, mzd_t *B, int const cutoff) {                                    \
+    host_trsm(T, B, norm_cutoff(cutoff < 0 ? 0 : cutoff, "_mzd_" #NAME), UPPER, LEFT);              \
+  }
+M4B_TRSM_ENTRY(trsm_lower_left, false, true)
+M4B_TRSM_ENTRY(trsm_upper_left, true, true)
+M4B_TRSM_ENTRY(trsm_lower_right, false, false)
+M4B_TRSM_ENTRY(trsm_upper_right, true, false)
+#undef M4B_TRSM_ENTRY
 
 // Row-blocks of C over the GPUs chosen with m4ri_b200_set_num_devices (multi.cu); one GPU: same as mzd_mul.
 mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
@@ -593,13 +594,16 @@ void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200
   device_product(C, A, B, levels, clear != 0, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
 }
 
-void m4ri_b200_dtrsm_left(m4ri_b200_dmat const *T, m4ri_b200_dmat *B, int upper, int cutoff, void *stream) {
-  if (T->nrows != T->ncols || T->ncols != B->nrows) die("m4ri_b200_dtrsm_left: dimension mismatch\n");
+void m4ri_b200_dtrsm(m4ri_b200_dmat const *T, m4ri_b200_dmat *B, int upper, int left, int cutoff, void *stream) {
+  if (T->nrows != T->ncols || (left ? T->ncols != B->nrows : T->nrows != B->ncols))
+    die("m4ri_b200_dtrsm: dimension mismatch\n");
   Ctx &c = ctx();
-  cutoff = norm_cutoff(cutoff, "m4ri_b200_dtrsm_left");
-  c.ws.reserve(trsm_workspace_bytes(B->nrows, B->ncols, cutoff));
-  snprintf(c.last_path, sizeof c.last_path, upper ? "trsm_upper_left" : "trsm_lower_left");
-  trsm_left(as_view(T), as_view(B), upper != 0, cutoff, c.ws, stream ? static_cast<cudaStream_t>(stream) : c.stream);
+  cutoff = norm_cutoff(cutoff, "m4ri_b200_dtrsm");
+  c.ws.reserve(trsm_workspace_bytes(T->nrows, B->nrows, B->ncols, cutoff));
+  snprintf(c.last_path, sizeof c.last_path, "trsm_%s_%s", upper ? "upper" : "lower", left ? "left" : "right");
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c.stream;
+  if (left) trsm_left(as_view(T), as_view(B), upper != 0, cutoff, c.ws, s);
+  else      trsm_right(as_view(T), as_view(B), upper != 0, cutoff, c.ws, s);
 }
 
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {

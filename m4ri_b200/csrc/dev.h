@@ -89,7 +89,8 @@ void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &
 
 // ---- triangular solve, left variants (trsm.cu) -----------------------------------------------
 // T: m x m (strict triangle read, unit diagonal implied), B: m x n, X overwrites B.
-void   trsm_left(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s);
-size_t trsm_workspace_bytes(int m, int n, int cutoff);
+void   trsm_left(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s);    // T X = B
+void   trsm_right(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s);   // X T = B
+size_t trsm_workspace_bytes(int t, int m, int n, int cutoff);
 
 }  // namespace m4b

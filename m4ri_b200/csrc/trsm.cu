@@ -62,11 +62,13 @@ void addmul_views(DView C, DView A, DView B, int cutoff, Workspace &ws, cudaStre
 
 }  // namespace
 
-size_t trsm_workspace_bytes(int m, int n, int cutoff) {
-  // every update product is at most m x m x n; its Strassen temporaries bound all the smaller ones
-  int const mp = (m + 127) / 128 * 128, np = (n + 127) / 128 * 128;
-  return strassen_workspace_bytes(mp, mp, np, strassen_levels(m, m, n, cutoff)) + Workspace::bytes_for(m, kBaseRows) +
-         Workspace::bytes_for(kBaseRows, n);
+// t = order of the triangular matrix, (m, n) = shape of B (left variants: t == m, right: t == n)
+size_t trsm_workspace_bytes(int t, int m, int n, int cutoff) {
+  // every update product is bounded by max-dims; its Strassen temporaries bound all the smaller ones
+  int const a = (t > m ? t : m), b = (t > n ? t : n);
+  int const ap = (a + 127) / 128 * 128, bp = (b + 127) / 128 * 128;
+  return strassen_workspace_bytes(ap, bp, bp, strassen_levels(a, b, b, cutoff)) + Workspace::bytes_for(t, kBaseRows) +
+         Workspace::bytes_for(m, kBaseRows) + Workspace::bytes_for(kBaseRows, n);
 }
 
 namespace {
@@ -100,12 +102,37 @@ void trsm_rec(DView T, DView B, DView Tinv, int row0, bool upper, int cutoff, Wo
   }
 }
 
-}  // namespace
-
-void trsm_left(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s) {
+// right variants, X T = B (m4ri/triangular.c:40-148, 300-392): the recursion runs over column blocks
+//     upper:  X0 = B0 T00^-1 ;  B1 ^= X0 T01 ;  X1 = B1 T11^-1
+//     lower:  X1 = B1 T11^-1 ;  B0 ^= X1 T10 ;  X0 = B0 T00^-1
+// col0 = first column of this sub-problem inside the whole B (= first row of its blocks in Tinv)
+void trsm_right_rec(DView T, DView B, DView Tinv, int col0, bool upper, int cutoff, Workspace &ws, cudaStream_t s) {
   int const m = B.nrows, n = B.ncols;
-  if (m <= 0 || n <= 0) return;
-  size_t const mark = ws.mark();
+  if (n <= kBaseRows) {
+    size_t const mark = ws.mark();
+    DView X = ws.alloc(m, n);
+    launch_zero(X, s);
+    launch_m4rm(X, B, Tinv.sub(col0, 0, col0 + n, n), s);       // X = B_block * inv(T_block)
+    launch_copy(B, X, s);
+    ws.release(mark);
+    return;
+  }
+  int const n1 = ((n + 127) / 128 / 2) * 128;
+  DView const T00 = T.sub(0, 0, n1, n1), T11 = T.sub(n1, n1, n, n);
+  DView const B0 = B.sub(0, 0, m, n1), B1 = B.sub(0, n1, m, n);
+  if (upper) {
+    trsm_right_rec(T00, B0, Tinv, col0, true, cutoff, ws, s);
+    addmul_views(B1, B0, T.sub(0, n1, n1, n), cutoff, ws, s);
+    trsm_right_rec(T11, B1, Tinv, col0 + n1, true, cutoff, ws, s);
+  } else {
+    trsm_right_rec(T11, B1, Tinv, col0 + n1, false, cutoff, ws, s);
+    addmul_views(B0, B1, T.sub(n1, 0, n, n1), cutoff, ws, s);
+    trsm_right_rec(T00, B0, Tinv, col0, false, cutoff, ws, s);
+  }
+}
+
+DView invert_diagonal_blocks(DView T, bool upper, Workspace &ws, cudaStream_t s) {
+  int const m = T.nrows;
   DView Tinv = ws.alloc(m, kBaseRows);
   unsigned const blocks = (m + kBaseRows - 1) / kBaseRows;
   auto const *t = reinterpret_cast<uint32_t const *>(T.data);
@@ -114,6 +141,24 @@ void trsm_left(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStre
   else       tri_inv128_kernel<false><<<blocks, 32, 0, s>>>(t, T.pitch * 2, inv, m);
   M4B_CUDA(cudaGetLastError());
   ++g_kernel_launches;
+  return Tinv;
+}
+
+}  // namespace
+
+void trsm_right(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s) {
+  if (B.nrows <= 0 || B.ncols <= 0) return;
+  size_t const mark = ws.mark();
+  DView Tinv = invert_diagonal_blocks(T, upper, ws, s);
+  trsm_right_rec(T, B, Tinv, 0, upper, cutoff, ws, s);
+  ws.release(mark);
+}
+
+void trsm_left(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s) {
+  int const m = B.nrows, n = B.ncols;
+  if (m <= 0 || n <= 0) return;
+  size_t const mark = ws.mark();
+  DView Tinv = invert_diagonal_blocks(T, upper, ws, s);
   trsm_rec(T, B, Tinv, 0, upper, cutoff, ws, s);
   ws.release(mark);
 }

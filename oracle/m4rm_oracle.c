@@ -464,3 +464,37 @@ void orc_trsm_upper_left(orc_mzd const *U, orc_mzd *B) {
     for (orc_rci k = i + 1; k < B->nrows; ++k)
       if ((rowp(U, i)[k / RADIX] >> (k % RADIX)) & 1) xor_row_valid(B, i, k);
 }
+
+/* right variants, X U = B / X L = B (triangular.c:29-148, 300-392): once column k of X is final, every
+ * row of B whose bit k is set receives row k of the triangular matrix restricted to its strict
+ * triangle (columns > k for U, ascending k; columns < k for L, descending k). */
+static void xor_tri_row(orc_mzd *B, orc_rci i, orc_mzd const *T, orc_rci k, int upper) {
+  orc_word *d = rowp(B, i);
+  orc_word const *t = rowp(T, k);
+  orc_rci const n = B->ncols;
+  for (orc_wi w = 0; w < B->width; ++w) {
+    orc_word mask = ~(orc_word)0;
+    orc_rci const lo = (orc_rci)(w * RADIX);              /* first column of this word */
+    if (upper) {                                           /* keep columns > k */
+      if (lo + RADIX - 1 <= k) mask = 0;
+      else if (lo <= k) mask = ~(orc_word)0 << (k - lo) << 1;
+    } else {                                               /* keep columns < k */
+      if (lo >= k) mask = 0;
+      else if (lo + RADIX > k) mask = ((orc_word)1 << (k - lo)) - 1;
+    }
+    if (lo + RADIX > n) mask &= left_mask(n % RADIX);      /* columns >= n do not exist */
+    d[w] ^= t[w] & mask;
+  }
+}
+
+void orc_trsm_upper_right(orc_mzd const *U, orc_mzd *B) {
+  for (orc_rci k = 0; k < B->ncols; ++k)
+    for (orc_rci i = 0; i < B->nrows; ++i)
+      if ((rowp(B, i)[k / RADIX] >> (k % RADIX)) & 1) xor_tri_row(B, i, U, k, 1);
+}
+
+void orc_trsm_lower_right(orc_mzd const *L, orc_mzd *B) {
+  for (orc_rci k = B->ncols - 1; k >= 0; --k)
+    for (orc_rci i = 0; i < B->nrows; ++i)
+      if ((rowp(B, i)[k / RADIX] >> (k % RADIX)) & 1) xor_tri_row(B, i, L, k, 0);
+}

@@ -60,6 +60,9 @@ orc_mzd *orc_addmul(orc_mzd *C, orc_mzd const *A, orc_mzd const *B, int cutoff);
 /* L X = B / U X = B, X overwrites B; unit diagonal implied (m4ri/triangular.c:406-516) */
 void     orc_trsm_lower_left(orc_mzd const *L, orc_mzd *B);
 void     orc_trsm_upper_left(orc_mzd const *U, orc_mzd *B);
+/* X L = B / X U = B (m4ri/triangular.c:29-148, 300-392) */
+void     orc_trsm_lower_right(orc_mzd const *L, orc_mzd *B);
+void     orc_trsm_upper_right(orc_mzd const *U, orc_mzd *B);
 
 #ifdef __cplusplus
 }

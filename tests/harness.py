@@ -54,6 +54,8 @@ def oracle():
         lib.orc_addmul.argtypes, lib.orc_addmul.restype = [MzdP, MzdP, MzdP, c_int], MzdP
         lib.orc_trsm_lower_left.argtypes = [MzdP, MzdP]
         lib.orc_trsm_upper_left.argtypes = [MzdP, MzdP]
+        lib.orc_trsm_lower_right.argtypes = [MzdP, MzdP]
+        lib.orc_trsm_upper_right.argtypes = [MzdP, MzdP]
         _oracle = lib
     return _oracle
 

@@ -22,34 +22,26 @@ def lib():
 
 @pytest.mark.parametrize("shape", SHAPES + [(129, 200, 0, 0), (1000, 1000, 0, 0), (2500, 3000, 64, 64), (4096, 5000, 0, 0)])
 @pytest.mark.parametrize("side", ["lower", "upper"])
-def test_trsm_left_matches_oracle(lib, shape, side):
+@pytest.mark.parametrize("hand", ["left", "right"])
+def test_trsm_matches_oracle(lib, shape, side, hand):
     m, n, off_t, off_b = shape
-    Tbase, Bbase, T, B = make_case(m, n, off_t, off_b, 7 + m)
+    if hand == "right" and n > 3000:
+        n = 3000        # the oracle's right solve is O(m n^2 / 64) row operations
+    Tbase, Bbase, T, B = make_case(m, n, off_t, off_b, 7 + m, hand == "right")
     want_base = H.clone(Bbase)
     H.storage(want_base)[:, :] = H.storage(Bbase)
     want = H.window(want_base, 1, off_b, 1 + m, off_b + n)
     launches = lib.m4ri_b200_kernel_launches()
-    if side == "lower":
-        H.oracle().orc_trsm_lower_left(T, want)
-        lib.mzd_trsm_lower_left(T, B, 0)
-    else:
-        H.oracle().orc_trsm_upper_left(T, want)
-        lib.mzd_trsm_upper_left(T, B, 0)
+    getattr(H.oracle(), f"orc_trsm_{side}_{hand}")(T, want)
+    getattr(lib, f"mzd_trsm_{side}_{hand}")(T, B, 0)
+    assert lib.m4ri_b200_last_path().decode() == f"trsm_{side}_{hand}"
     assert lib.m4ri_b200_kernel_launches() > launches
     assert np.array_equal(H.storage(Bbase), H.storage(want_base))   # incl. every bit outside the window
     H.free(T, B, want, Tbase, Bbase, want_base)
 
 
-@pytest.mark.parametrize("m,n", [(16384, 16384), (20000, 4100)])
-@pytest.mark.parametrize("side", ["lower", "upper"])
-def test_trsm_left_large_property(lib, m, n, side):
-    """T * X == B0 checked with 24 random vectors: (T x_col)... on the right: T (X v) == B0 v."""
-    T, B = H.new(m, m), H.new(m, n)
-    _fill_fast(T, 5); _fill_fast(B, 6)
-    B0 = m4ri_b200.valid_words(B)
-    (lib.mzd_trsm_lower_left if side == "lower" else lib.mzd_trsm_upper_left)(T, B, 0)
-    # effective triangular matrix: strict triangle of T plus unit diagonal
-    Tw = m4ri_b200.valid_words(T)
+def _effective_triangle(Tw, m, side):
+    """strict triangle of the bit-packed square matrix Tw plus the unit diagonal"""
     rows = np.arange(m)
     colword = (np.arange(Tw.shape[1], dtype=np.int64) * 64)[None, :]
     rel = rows[:, None] - colword                 # diagonal position relative to each word
@@ -65,12 +57,27 @@ def test_trsm_left_large_property(lib, m, n, side):
         mask = np.where(part, ~((np.uint64(1) << np.clip(rel, 0, 63).astype(np.uint64)) - np.uint64(1)), mask)
     Teff = Tw & mask
     Teff[rows, rows // 64] |= np.uint64(1) << (rows % 64).astype(np.uint64)
+    return Teff
+
+
+@pytest.mark.parametrize("m,n", [(16384, 16384), (20000, 4100)])
+@pytest.mark.parametrize("side", ["lower", "upper"])
+@pytest.mark.parametrize("hand", ["left", "right"])
+def test_trsm_large_property(lib, m, n, side, hand):
+    """left: T (X v) == B0 v;  right: X (T v) == B0 v, for 24 random vectors v (independent numpy mat-vecs)."""
+    t = m if hand == "left" else n
+    T, B = H.new(t, t), H.new(m, n)
+    _fill_fast(T, 5); _fill_fast(B, 6)
+    B0 = m4ri_b200.valid_words(B)
+    getattr(lib, f"mzd_trsm_{side}_{hand}")(T, B, 0)
+    Teff = _effective_triangle(m4ri_b200.valid_words(T), t, side)
     Xw = m4ri_b200.valid_words(B)
     rng = np.random.default_rng(9)
     for _ in range(24):
         v = rng.integers(0, 2, size=n).astype(bool)
-        xv = _gf2_matvec_rows(Xw, _pack(v))
-        lhs = _gf2_matvec_rows(Teff, _pack(xv))
-        rhs = _gf2_matvec_rows(B0, _pack(v))
-        assert np.array_equal(lhs, rhs)
+        if hand == "left":
+            lhs = _gf2_matvec_rows(Teff, _pack(_gf2_matvec_rows(Xw, _pack(v))))
+        else:
+            lhs = _gf2_matvec_rows(Xw, _pack(_gf2_matvec_rows(Teff, _pack(v))))
+        assert np.array_equal(lhs, _gf2_matvec_rows(B0, _pack(v)))
     H.free(T, B)

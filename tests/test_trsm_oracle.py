@@ -13,10 +13,12 @@ SHAPES = [(10, 20, 0, 0), (10, 80, 0, 0), (70, 20, 0, 0), (70, 80, 0, 0), (53, 5
           (1764, 1345, 128, 64), (1, 1, 0, 0), (2, 300, 0, 0)]
 
 
-def make_case(m, n, off_t, off_b, seed):
+def make_case(m, n, off_t, off_b, seed, right=False):
+    """left: T is m x m, B is m x n.  right: T is n x n, B is m x n."""
     H.libc.srandom(seed)
-    Tbase, Bbase = H.random_matrix(m + 3, m + off_t + 64), H.random_matrix(m + 3, n + off_b + 64)
-    T = H.window(Tbase, 1, off_t, 1 + m, off_t + m)      # random bits everywhere: diagonal and the other
+    t = n if right else m
+    Tbase, Bbase = H.random_matrix(t + 3, t + off_t + 64), H.random_matrix(m + 3, n + off_b + 64)
+    T = H.window(Tbase, 1, off_t, 1 + t, off_t + t)      # random bits everywhere: diagonal and the other
     B = H.window(Bbase, 1, off_b, 1 + m, off_b + n)      # triangle must be ignored by the solver
     return Tbase, Bbase, T, B
 
@@ -24,18 +26,21 @@ def make_case(m, n, off_t, off_b, seed):
 @needs_ref
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("side", ["lower", "upper"])
-def test_oracle_trsm_left_matches_compiled_reference(shape, side):
+@pytest.mark.parametrize("hand", ["left", "right"])
+def test_oracle_trsm_matches_compiled_reference(shape, side, hand):
     m, n, off_t, off_b = shape
+    right = hand == "right"
     O, R = H.oracle(), H.ref()
-    Tbase, Bbase, T, B = make_case(m, n, off_t, off_b, 100 + m + n)
+    Tbase, Bbase, T, B = make_case(m, n, off_t, off_b, 100 + m + n, right)
+    m_t = n if right else m
     # the reference requires a proper triangular matrix with unit diagonal: give it one, but keep the
     # garbage for the oracle to prove the garbage is ignored
     Tclean_base = H.clone(Tbase)
     H.storage(Tclean_base)[:, :] = H.storage(Tbase)
-    Tclean = H.window(Tclean_base, 1, off_t, 1 + m, off_t + m)
+    Tclean = H.window(Tclean_base, 1, off_t, 1 + m_t, off_t + m_t)
     tw = H.storage(Tclean_base)
-    for i in range(m):
-        for j in range(m):
+    for i in range(m_t):
+        for j in range(m_t):
             keep = (j < i) if side == "lower" else (j > i)
             if not keep:
                 col = off_t + j
@@ -45,11 +50,7 @@ def test_oracle_trsm_left_matches_compiled_reference(shape, side):
     Bref_base = H.clone(Bbase)
     H.storage(Bref_base)[:, :] = H.storage(Bbase)
     Bref = H.window(Bref_base, 1, off_b, 1 + m, off_b + n)
-    if side == "lower":
-        O.orc_trsm_lower_left(T, B)
-        R.mzd_trsm_lower_left(Tclean, Bref, 0)
-    else:
-        O.orc_trsm_upper_left(T, B)
-        R.mzd_trsm_upper_left(Tclean, Bref, 0)
+    getattr(O, f"orc_trsm_{side}_{hand}")(T, B)
+    getattr(R, f"mzd_trsm_{side}_{hand}")(Tclean, Bref, 0)
     assert np.array_equal(H.storage(Bbase), H.storage(Bref_base))   # also: nothing outside the window moved
     H.free(T, B, Tclean, Bref, Tbase, Bbase, Tclean_base, Bref_base)

@@ -28,19 +28,19 @@ def dev_random(rows, cols):
 for m, n in [(16384, 16384), (65536, 65536)]:
     tT, dT = dev_random(m, m)
     tB, dB = dev_random(m, n)
-    for upper in (0, 1):
+    for upper, left in ((0, 1), (1, 1), (0, 0), (1, 0)):
         for _ in range(2):
-            lib.m4ri_b200_dtrsm_left(dT, dB, upper, 0, sh)
+            lib.m4ri_b200_dtrsm(dT, dB, upper, left, 0, sh)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.m4ri_b200_kernel_launches()
         e0.record()
         for _ in range(3):
-            lib.m4ri_b200_dtrsm_left(dT, dB, upper, 0, sh)
+            lib.m4ri_b200_dtrsm(dT, dB, upper, left, 0, sh)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
-        print(f"device trsm_{'upper' if upper else 'lower'}_left m={m} n={n}: {ms:.2f} ms "
+        print(f"device trsm_{'upper' if upper else 'lower'}_{'left' if left else 'right'} m={m} n={n}: {ms:.2f} ms "
               f"({1.0*m*m*n/ms/1e9:.0f} T bit-ops/s nominal m^2 n) launches/call {(lib.m4ri_b200_kernel_launches()-l0)//3}", flush=True)
     del tT, tB
 
