@@ -44,6 +44,8 @@ extern unsigned long long g_kernel_launches;  // counted by every launcher in th
 void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream);
 // up to 7 products of identical shape in ONE persistent launch (the last Strassen level)
 void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream);
+// C = A*B for l <= 128 with plain stores; C may alias A or B
+void launch_m4rm_overwrite(DView C, DView A, DView B, cudaStream_t stream);
 int  m4rm_num_sms();
 void leaf_profile_begin();
 unsigned long long leaf_profile_end(double *ms, double *bitops);

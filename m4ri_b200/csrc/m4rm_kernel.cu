@@ -61,6 +61,8 @@ struct alignas(64) BatchArgs {
   int tiles_n;
   int slabs;            // ceil(l / 128)
   int nprob;
+  int overwrite;        // 1: C = A*B with plain stores (only legal when slabs == 1: every tile has one owner);
+                        //    C may then alias A or B (the owner has consumed its operands before it stores)
   long long units_per_problem;   // tiles_m * tiles_n * slabs
   long long total_units;         // nprob * units_per_problem
 };
@@ -296,8 +298,13 @@ m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
           for (int h = 0; h < 2; ++h) {
             int const wcol = tn * (kTileBits / 64) + (hi ^ h) * 8 + c4 * 2;
             unsigned long long *dst = p.C[prob] + (long long)row * p.pitchC[prob] + wcol;
-            if (wcol < p.nwordsC) red_xor64(dst, acc[j][h].x, acc[j][h].y);
-            if (wcol + 1 < p.nwordsC) red_xor64(dst + 1, acc[j][h].z, acc[j][h].w);
+            if (p.overwrite) {
+              if (wcol < p.nwordsC) dst[0] = ((unsigned long long)acc[j][h].y << 32) | acc[j][h].x;
+              if (wcol + 1 < p.nwordsC) dst[1] = ((unsigned long long)acc[j][h].w << 32) | acc[j][h].z;
+            } else {
+              if (wcol < p.nwordsC) red_xor64(dst, acc[j][h].x, acc[j][h].y);
+              if (wcol + 1 < p.nwordsC) red_xor64(dst + 1, acc[j][h].z, acc[j][h].w);
+            }
           }
         }
       }
@@ -342,7 +349,7 @@ CUtensorMap make_map(DView V, int box_w32, int box_rows) {
 }
 
 template <int TM, int NT>
-void launch_variant(int count, DView const *Cv, DView const *A, DView const *B, cudaStream_t stream) {
+void launch_variant(int count, DView const *Cv, DView const *A, DView const *B, bool overwrite, cudaStream_t stream) {
   using C = Cfg<TM, NT>;
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
   auto kern = m4rm_streamk_kernel<TM, NT>;
@@ -359,6 +366,8 @@ void launch_variant(int count, DView const *Cv, DView const *A, DView const *B, 
   p.tiles_n = (B[0].ncols + kTileBits - 1) / kTileBits;
   p.slabs = (A[0].ncols + kSlabBits - 1) / kSlabBits;
   p.nprob = count;
+  p.overwrite = overwrite ? 1 : 0;
+  if (overwrite && p.slabs != 1) die("m4ri_b200: overwrite mode needs a single K slab\n");
   p.units_per_problem = (long long)p.tiles_m * p.tiles_n * p.slabs;
   p.total_units = p.units_per_problem * count;
   for (int i = 0; i < count; ++i) {
@@ -420,7 +429,7 @@ int m4rm_num_sms() {
   return sms;
 }
 
-void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream) {
+static void launch_leaf(int count, DView const *C, DView const *A, DView const *B, bool overwrite, cudaStream_t stream) {
   if (count <= 0 || A[0].nrows <= 0 || A[0].ncols <= 0 || B[0].ncols <= 0) return;   // empty product: C unchanged
   if (count > kMaxBatch) die("m4ri_b200: batch of %d leaf products exceeds %d\n", count, kMaxBatch);
   std::pair<cudaEvent_t, cudaEvent_t> *ev = nullptr;
@@ -436,12 +445,23 @@ void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B
     M4B_CUDA(cudaEventRecord(ev->first, stream));
   }
   if (A[0].nrows <= 256)
-    launch_variant<256, 256>(count, C, A, B, stream);     // short operands: 256-row tiles
+    launch_variant<256, 256>(count, C, A, B, overwrite, stream);     // short operands: 256-row tiles
   else
-    launch_variant<1024, 256>(count, C, A, B, stream);
+    launch_variant<1024, 256>(count, C, A, B, overwrite, stream);
   if (ev) M4B_CUDA(cudaEventRecord(ev->second, stream));
 }
 
-void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) { launch_m4rm_batch(1, &C, &A, &B, stream); }
+void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream) {
+  launch_leaf(count, C, A, B, false, stream);
+}
+
+void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) { launch_leaf(1, &C, &A, &B, false, stream); }
+
+// C = A*B for an inner dimension of at most 128 (one K slab): plain stores, no zero fill needed, and C
+// may be the same view as A or B (used by the triangular solves for X = inv(T_block) * B_block in place).
+void launch_m4rm_overwrite(DView C, DView A, DView B, cudaStream_t stream) {
+  if (A.ncols > kSlabBits) die("m4ri_b200: launch_m4rm_overwrite needs l <= 128\n");
+  launch_leaf(1, &C, &A, &B, true, stream);
+}
 
 }  // namespace m4b

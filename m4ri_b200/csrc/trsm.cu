@@ -79,13 +79,9 @@ void trsm_rec(DView T, DView B, DView Tinv, int row0, bool upper, int cutoff, Wo
   int const m = B.nrows, n = B.ncols;
   if (m <= kBaseRows) {
     // X = inv(T_block) * B_block: one 128-row product of the M4RM leaf (full-chip parallel over the
-    // columns of B), through a temporary because the kernel cannot read and accumulate in place
-    size_t const mark = ws.mark();
-    DView X = ws.alloc(m, n);
-    launch_zero(X, s);
-    launch_m4rm(X, Tinv.sub(row0, 0, row0 + m, m), B, s);
-    launch_copy(B, X, s);
-    ws.release(mark);
+    // columns of B), IN PLACE: with a single K slab every C tile has one owner CTA, which has staged its
+    // whole B column strip before it stores
+    launch_m4rm_overwrite(B, Tinv.sub(row0, 0, row0 + m, m), B, s);
     return;
   }
   int const m1 = ((m + 127) / 128 / 2) * 128;          // multiple of 128, 0 < m1 < m
@@ -109,12 +105,7 @@ void trsm_rec(DView T, DView B, DView Tinv, int row0, bool upper, int cutoff, Wo
 void trsm_right_rec(DView T, DView B, DView Tinv, int col0, bool upper, int cutoff, Workspace &ws, cudaStream_t s) {
   int const m = B.nrows, n = B.ncols;
   if (n <= kBaseRows) {
-    size_t const mark = ws.mark();
-    DView X = ws.alloc(m, n);
-    launch_zero(X, s);
-    launch_m4rm(X, B, Tinv.sub(col0, 0, col0 + n, n), s);       // X = B_block * inv(T_block)
-    launch_copy(B, X, s);
-    ws.release(mark);
+    launch_m4rm_overwrite(B, B, Tinv.sub(col0, 0, col0 + n, n), s);   // X = B_block * inv(T_block), in place
     return;
   }
   int const n1 = ((n + 127) / 128 / 2) * 128;
