@@ -395,6 +395,24 @@ def run_own_arm(args):
                 "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src},
     }
 
+    # ---- the HBM-bound kernel of the path: the device _mzd_add (C = A ^ B) on the full operands ----------
+    add_roofline = None
+    if world == 1:
+        for _ in range(3):
+            lib.m4ri_b200_dadd(dC, dA, dB, sh)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            lib.m4ri_b200_dadd(dC, dA, dB, sh)
+        a1.record()
+        torch.cuda.synchronize()
+        add_ms = a0.elapsed_time(a1) / 10
+        add_bytes = 3.0 * rows * pitch * 8           # 2 reads + 1 write, every byte once
+        add_gbs = add_bytes / (add_ms * 1e-3) / 1e9
+        add_roofline = {"kernel": "ew_kernel<0> (_mzd_add)", "bound": "hbm", "unit": "GB/s", "achieved": add_gbs,
+                        "peak": hbm_peak, "frac": add_gbs / hbm_peak, "ms": add_ms,
+                        "algorithmic_bytes_per_launch": add_bytes, "peak_source": peak_src}
+
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -415,6 +433,8 @@ def run_own_arm(args):
                 "upload + all_gather + m4ri_b200_dmul + download per rank"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
     }
+    if add_roofline is not None:
+        line["roofline_add"] = add_roofline
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
