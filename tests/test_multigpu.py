@@ -20,7 +20,8 @@ def lib():
 
 
 @pytest.mark.parametrize("shape,cutoff", [((300, 200, 260), 0), ((130, 1000, 70), 0), ((1, 64, 64), 0),
-                                          ((4100, 3000, 2500), 1024), ((2048, 2048, 2048), 512), ((70, 4096, 4096), 0)])
+                                          ((4100, 3000, 2500), 1024), ((2048, 2048, 2048), 512), ((70, 4096, 4096), 0),
+                                          ((9000, 8200, 8300), 2048)])   # large enough for the per-GPU staging rings
 def test_mul_mp_matches_oracle_for_every_device_count(lib, shape, cutoff):
     m, l, n = shape
     H.libc.srandom(21)

@@ -384,3 +384,28 @@ def test_fuzz_random_shapes_windows_and_entry_points(lib):
         H.free(Cw)
         if ref_parent is not None:
             H.free(ref_parent)
+
+
+@pytest.mark.parametrize("fn", ["mzd_mul", "mzd_addmul"])
+def test_large_pageable_windows_go_through_the_staging_ring(lib, fn):
+    """Operands big enough (> 4 MiB) to take the pinned staging path (csrc/staging.cu), as WINDOWS of
+    pageable parents: foreign row stride, odd word offsets, partial last words — every bit outside C's
+    window must survive, the result must equal the oracle's."""
+    m, l, n = 6100, 7000, 6500
+    rng = np.random.default_rng(77)
+
+    def windowed(rows, cols, off_r, off_w):
+        P = H.new(rows + off_r + 1, (cols + 63) // 64 * 64 + 64 * (off_w + 2))
+        H.storage(P)[:, :] = rng.integers(0, 2**64, size=H.storage(P).shape, dtype=np.uint64)
+        return P, H.window(P, off_r, 64 * off_w, off_r + rows, 64 * off_w + cols)
+
+    PA, A = windowed(m, l, 1, 1)
+    PB, B = windowed(l, n, 2, 3)
+    PC, C = windowed(m, n, 1, 2)
+    want_parent = H.clone(PC)
+    H.storage(want_parent)[:, :] = H.storage(PC)
+    Cw = H.window(want_parent, 1, 128, 1 + m, 128 + n)
+    (H.oracle().orc_mul if fn == "mzd_mul" else H.oracle().orc_addmul)(Cw, A, B, 0)
+    getattr(lib, fn)(C, A, B, 2048)
+    assert np.array_equal(H.storage(PC), H.storage(want_parent))
+    H.free(A, B, C, Cw, PA, PB, PC, want_parent)
