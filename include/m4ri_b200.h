@@ -141,6 +141,10 @@ void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200
 /* T X = B (left != 0) or X T = B (left == 0) on device matrices, T lower triangular or upper if
  * upper != 0; X overwrites B. */
 void m4ri_b200_dtrsm(m4ri_b200_dmat const *T, m4ri_b200_dmat *B, int upper, int left, int cutoff, void *stream);
+/* DST = A^T on device matrices (DST must not alias A), and the host form with mzd_transpose's semantics
+ * (m4ri/mzd.c:1118-1139; DST may be NULL).  Not exported as mzd_transpose: libm4ri keeps its own. */
+void   m4ri_b200_dtranspose(m4ri_b200_dmat *DST, m4ri_b200_dmat const *A, void *stream);
+mzd_t *m4ri_b200_transpose(mzd_t *DST, mzd_t const *A);
 /* C = A ^ B on device matrices (the device form of _mzd_add, m4ri/mzd.c:1471-1583). */
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream);
 

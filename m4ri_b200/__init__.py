@@ -94,6 +94,8 @@ def _declare(lib):
     lib.m4ri_b200_dmul_m4rm.argtypes = [DMatP, DMatP, DMatP, c_int, c_void_p]
     lib.m4ri_b200_dmul.argtypes = [DMatP, DMatP, DMatP, c_int, c_int, c_void_p]
     lib.m4ri_b200_dmul_levels.argtypes = [DMatP, DMatP, DMatP, c_int, c_int, c_void_p]
+    lib.m4ri_b200_dtranspose.argtypes = [DMatP, DMatP, c_void_p]
+    lib.m4ri_b200_transpose.argtypes, lib.m4ri_b200_transpose.restype = [MzdP, MzdP], MzdP
     lib.m4ri_b200_dadd.argtypes = [DMatP, DMatP, DMatP, c_void_p]
     return lib
 

@@ -606,6 +606,33 @@ void m4ri_b200_dtrsm(m4ri_b200_dmat const *T, m4ri_b200_dmat *B, int upper, int 
   else      trsm_right(as_view(T), as_view(B), upper != 0, cutoff, c.ws, s);
 }
 
+void m4ri_b200_dtranspose(m4ri_b200_dmat *DST, m4ri_b200_dmat const *A, void *stream) {
+  if (DST->nrows != A->ncols || DST->ncols != A->nrows) die("m4ri_b200_dtranspose: Wrong size for return matrix.\n");
+  if (DST->data == A->data) die("m4ri_b200_dtranspose: DST must not alias A\n");
+  launch_transpose(as_view(DST), as_view(A), stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+}
+
+// Host form with the reference's semantics (mzd_transpose, m4ri/mzd.c:1118-1139): DST may be NULL
+// (allocated), wrong dimensions die, only DST's valid bits are written.
+mzd_t *m4ri_b200_transpose(mzd_t *DST, mzd_t const *A) {
+  if (DST == NULL) DST = alloc_result(A->ncols, A->nrows);
+  else if (DST->nrows != A->ncols || DST->ncols != A->nrows) die("mzd_transpose: Wrong size for return matrix.\n");
+  if (A->nrows == 0 || A->ncols == 0) return DST;
+  Ctx &c = ctx();
+  ++g_products;
+  snprintf(c.last_path, sizeof c.last_path, "transpose");
+  c.ws.reserve(Workspace::bytes_for(A->nrows, A->ncols) + Workspace::bytes_for(A->ncols, A->nrows));
+  cudaStream_t s = c.stream;
+  DView dA = c.ws.alloc(A->nrows, A->ncols), dD = c.ws.alloc(A->ncols, A->nrows);
+  zero_async(dA, s);
+  upload(dA, A, s, &c.stager);
+  launch_transpose(dD, dA, s);
+  download(DST, dD, s, c.host_tmp, &c.stager);
+  M4B_CUDA(cudaStreamSynchronize(s));
+  c.ws.release(0);
+  return DST;
+}
+
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {
   if (A->nrows != B->nrows || A->ncols != B->ncols || C->nrows != A->nrows || C->ncols != A->ncols)
     die("m4ri_b200_dadd: dimension mismatch\n");

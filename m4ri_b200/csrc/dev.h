@@ -55,6 +55,7 @@ void launch_xor(DView C, DView A, DView B, cudaStream_t stream);        // C = A
 void launch_zero(DView C, cudaStream_t stream);                          // C = 0
 void launch_copy(DView C, DView A, cudaStream_t stream);                 // C = A
 void launch_mask_excess(DView C, cudaStream_t stream);                   // clear bits >= ncols of last word(s)
+void launch_transpose(DView dst, DView src, cudaStream_t stream);        // dst = src^T (transpose.cu)
 // fused additions of one Strassen-Winograd node (quadrant order 11, 12, 21, 22)
 void launch_winograd_pre_a(DView const a[4], DView const s_out[4], cudaStream_t stream);
 void launch_winograd_pre_b(DView const b[4], DView const t_out[4], cudaStream_t stream);

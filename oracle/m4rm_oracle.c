@@ -498,3 +498,16 @@ void orc_trsm_lower_right(orc_mzd const *L, orc_mzd *B) {
     for (orc_rci i = 0; i < B->nrows; ++i)
       if ((rowp(B, i)[k / RADIX] >> (k % RADIX)) & 1) xor_tri_row(B, i, L, k, 0);
 }
+
+/* ---- transpose (m4ri/mzd.c:1118-1139): DST[j][i] = A[i][j], only DST's valid bits are written ---- */
+orc_mzd *orc_transpose(orc_mzd *D, orc_mzd const *A) {
+  if (!D) D = orc_init(A->ncols, A->nrows);
+  for (orc_rci j = 0; j < A->ncols; ++j) {
+    orc_word *d = rowp(D, j);
+    for (orc_rci i = 0; i < A->nrows; ++i) {
+      orc_word const bit = (rowp(A, i)[j / RADIX] >> (j % RADIX)) & 1;
+      d[i / RADIX] = (d[i / RADIX] & ~((orc_word)1 << (i % RADIX))) | (bit << (i % RADIX));
+    }
+  }
+  return D;
+}

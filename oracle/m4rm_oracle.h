@@ -64,6 +64,9 @@ void     orc_trsm_upper_left(orc_mzd const *U, orc_mzd *B);
 void     orc_trsm_lower_right(orc_mzd const *L, orc_mzd *B);
 void     orc_trsm_upper_right(orc_mzd const *U, orc_mzd *B);
 
+/* DST = A^T (m4ri/mzd.c:1118-1139) */
+orc_mzd *orc_transpose(orc_mzd *DST, orc_mzd const *A);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,7 @@ def oracle():
         lib.orc_trsm_upper_left.argtypes = [MzdP, MzdP]
         lib.orc_trsm_lower_right.argtypes = [MzdP, MzdP]
         lib.orc_trsm_upper_right.argtypes = [MzdP, MzdP]
+        lib.orc_transpose.argtypes, lib.orc_transpose.restype = [MzdP, MzdP], MzdP
         _oracle = lib
     return _oracle
 
@@ -80,6 +81,7 @@ def _declare_ref(lib):
     lib.m4ri_build_code.argtypes = [POINTER(c_int), POINTER(c_int), c_int]
     lib.mzd_make_table.argtypes = [MzdP, c_int, c_int, c_int, MzdP, POINTER(c_int)]
     lib.m4ri_random_word.restype = c_uint64
+    lib.mzd_transpose.argtypes, lib.mzd_transpose.restype = [MzdP, MzdP], MzdP
     for name in ("mzd_trsm_lower_left", "mzd_trsm_upper_left", "mzd_trsm_lower_right", "mzd_trsm_upper_right"):
         getattr(lib, name).argtypes = [MzdP, MzdP, c_int]
         getattr(lib, name).restype = None
