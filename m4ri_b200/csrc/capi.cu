@@ -102,7 +102,16 @@ mzd_t *alloc_result(rci_t r, rci_t c) {
 }  // namespace
 
 // ---- transfers (shared with multi.cu) ------------------------------------------------------
-constexpr size_t kStageThreshold = 4u << 20;   // below this the driver's own pageable path is as fast
+// below this size the driver's own pageable path is as fast as the staging ring (tunable for experiments)
+static size_t stage_threshold() {
+  static size_t v = 0;
+  if (!v) {
+    char const *env = getenv("M4RI_B200_STAGE_MIN");
+    v = env && atoll(env) > 0 ? (size_t)atoll(env) : (size_t)(4u << 20);
+  }
+  return v;
+}
+#define kStageThreshold stage_threshold()
 
 void upload(DView dst, mzd_t const *src, cudaStream_t s, Stager *st) {
   if (src->nrows == 0 || src->ncols == 0) return;
