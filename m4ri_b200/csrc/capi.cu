@@ -499,6 +499,12 @@ void m4ri_b200_release(void) {
   g.stager.release();
 }
 
+int m4ri_b200_set_leaf_variant(int variant) {
+  int const prev = g_leaf_variant;
+  g_leaf_variant = variant >= 0 && variant <= 2 ? variant : -1;    // -1: back to the environment / built-in default
+  return prev;
+}
+
 char const *m4ri_b200_last_path(void) { return g.last_path; }
 uint64_t    m4ri_b200_kernel_launches(void) { return g_kernel_launches; }
 

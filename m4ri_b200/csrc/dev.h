@@ -47,6 +47,11 @@ void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B
 // C = A*B for l <= 128 with plain stores; C may alias A or B
 void launch_m4rm_overwrite(DView C, DView A, DView B, cudaStream_t stream);
 int  m4rm_num_sms();
+// tall-tile leaf (m4rm_leaf2.cu): 4096 x 256-bit C tiles; worth it only when (nearly) all 4096 rows are real
+bool leaf2_suits(int m, int l, int n);
+void launch_m4rm_leaf2(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream);
+// 0 = automatic (leaf2 where it suits), 1 = always the 1024-row leaf, 2 = leaf2 whenever m >= 1
+extern int g_leaf_variant;
 void leaf_profile_begin();
 unsigned long long leaf_profile_end(double *ms, double *bitops);
 

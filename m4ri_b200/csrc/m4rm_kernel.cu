@@ -33,8 +33,42 @@
 #include <vector>
 
 #include "dev.h"
+#include "tmap.h"
 
 namespace m4b {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    M4B_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr));
+    if (!sym || qr != cudaDriverEntryPointSuccess) die("m4ri_b200: cuTensorMapEncodeTiled not available from the driver\n");
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2D map over u32 elements of a bit-packed view: dim0 = 32-bit words of the (128-bit padded)
+// row, dim1 = rows.  Reads outside [dim0) x [dim1) return zeros.
+CUtensorMap make_map(DView V, int box_w32, int box_rows) {
+  CUtensorMap map;
+  cuuint64_t dims[2]    = {(cuuint64_t)((V.ncols + 127) / 128) * 4, (cuuint64_t)V.nrows};
+  cuuint64_t strides[1] = {(cuuint64_t)V.pitch * 8};
+  cuuint32_t box[2]     = {(cuuint32_t)box_w32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, V.data, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    die("m4ri_b200: cuTensorMapEncodeTiled failed (%d) for view %p pitch %lld %dx%d\n", (int)r, (void *)V.data,
+        (long long)V.pitch, V.nrows, V.ncols);
+  return map;
+}
 
 namespace {
 
@@ -49,6 +83,9 @@ constexpr int kBSlabBytes = kSlabBits * kRowBytes;  // 16 KB
 // One launch multiplies up to kMaxBatch independent products of IDENTICAL shape (the seven products of
 // the last Strassen level): the stream-K unit space simply runs over (problem, tile, slab).
 constexpr int kMaxBatch = 7;
+
+// Until the tall-tile leaf has been timed and parity-checked on hardware the 1024-row leaf stays the default.
+constexpr int kDefaultLeafVariant = 1;
 
 struct alignas(64) BatchArgs {
   CUtensorMap mapA[kMaxBatch];
@@ -315,39 +352,6 @@ m4rm_streamk_kernel(const __grid_constant__ BatchArgs p) {
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void *sym = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    M4B_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr));
-    if (!sym || qr != cudaDriverEntryPointSuccess) die("m4ri_b200: cuTensorMapEncodeTiled not available from the driver\n");
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
-// 2D map over u32 elements of a bit-packed view: dim0 = 32-bit words of the (128-bit padded)
-// row, dim1 = rows.  Reads outside [dim0) x [dim1) return zeros.
-CUtensorMap make_map(DView V, int box_w32, int box_rows) {
-  CUtensorMap map;
-  cuuint64_t dims[2]    = {(cuuint64_t)((V.ncols + 127) / 128) * 4, (cuuint64_t)V.nrows};
-  cuuint64_t strides[1] = {(cuuint64_t)V.pitch * 8};
-  cuuint32_t box[2]     = {(cuuint32_t)box_w32, (cuuint32_t)box_rows};
-  cuuint32_t estr[2]    = {1, 1};
-  CUresult r = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, V.data, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    die("m4ri_b200: cuTensorMapEncodeTiled failed (%d) for view %p pitch %lld %dx%d\n", (int)r, (void *)V.data,
-        (long long)V.pitch, V.nrows, V.ncols);
-  return map;
-}
-
 template <int TM, int NT>
 void launch_variant(int count, DView const *Cv, DView const *A, DView const *B, bool overwrite, cudaStream_t stream) {
   using C = Cfg<TM, NT>;
@@ -429,6 +433,16 @@ int m4rm_num_sms() {
   return sms;
 }
 
+// Leaf selection: M4RI_B200_LEAF=0|1|2 in the environment, or m4ri_b200_set_leaf_variant() at run time.
+int g_leaf_variant = -1;
+static int leaf_variant() {
+  if (g_leaf_variant < 0) {
+    char const *env = getenv("M4RI_B200_LEAF");
+    g_leaf_variant = env && env[0] >= '0' && env[0] <= '2' && !env[1] ? env[0] - '0' : kDefaultLeafVariant;
+  }
+  return g_leaf_variant;
+}
+
 static void launch_leaf(int count, DView const *C, DView const *A, DView const *B, bool overwrite, cudaStream_t stream) {
   if (count <= 0 || A[0].nrows <= 0 || A[0].ncols <= 0 || B[0].ncols <= 0) return;   // empty product: C unchanged
   if (count > kMaxBatch) die("m4ri_b200: batch of %d leaf products exceeds %d\n", count, kMaxBatch);
@@ -444,7 +458,10 @@ static void launch_leaf(int count, DView const *C, DView const *A, DView const *
     g_prof.bitops += 2.0 * count * A[0].nrows * (double)A[0].ncols * B[0].ncols;
     M4B_CUDA(cudaEventRecord(ev->first, stream));
   }
-  if (A[0].nrows <= 256)
+  int const variant = leaf_variant();
+  if (!overwrite && (variant == 2 || (variant == 0 && leaf2_suits(A[0].nrows, A[0].ncols, B[0].ncols))))
+    launch_m4rm_leaf2(count, C, A, B, stream);                       // tall tiles: 4096 rows x 256 bits
+  else if (A[0].nrows <= 256)
     launch_variant<256, 256>(count, C, A, B, overwrite, stream);     // short operands: 256-row tiles
   else
     launch_variant<1024, 256>(count, C, A, B, overwrite, stream);

@@ -1,0 +1,148 @@
+// m4rm_leaf2.cu — device side and launcher of the tall-tile M4RM leaf (body: m4rm_leaf2_body.h).
+//
+// The body header is written against a handful of primitives so that the same source also runs inside
+// the CPU emulation harness tests/c/emu_leaf2.cpp; here they are the sm_100a instructions themselves:
+// LDS.128 / STS.128, PRMT, mbarrier try_wait / arrive.expect_tx, cp.async.bulk.tensor.2d (TMA),
+// red.global.xor.b64.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "dev.h"
+#include "tmap.h"
+
+#define L2_FN __device__ __forceinline__
+
+namespace leaf2 {
+
+typedef uint4 U4;
+typedef uint2 U2;
+typedef CUtensorMap TMap;
+
+L2_FN uint32_t smem_u32(void const *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+L2_FN U4 lds128(uint32_t addr) {
+  U4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+template <int IMM>
+L2_FN U4 lds128(uint32_t addr) {
+  U4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4 + %5];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr), "n"(IMM));
+  return v;
+}
+L2_FN U2 lds64(uint32_t addr) {
+  U2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+L2_FN void sts128(uint32_t addr, U4 const &v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+L2_FN uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+L2_FN void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+L2_FN void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+L2_FN void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+L2_FN void tma_load_2d(uint32_t dst, TMap const *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+L2_FN void red_xor64(unsigned long long *p, uint32_t lo, uint32_t hi) {
+  unsigned long long v = (static_cast<unsigned long long>(hi) << 32) | lo;
+  asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+L2_FN void cta_sync() { __syncthreads(); }
+L2_FN void warp_sync() { __syncwarp(); }
+
+}  // namespace leaf2
+
+#include "m4rm_leaf2_body.h"
+
+namespace leaf2 {
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) m4rm_leaf2_kernel(const __grid_constant__ Args p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint32_t const sbase = smem_u32(smem);
+  if (threadIdx.x == 0) {
+    mbar_init(sbase + kOffBar, 1);
+    mbar_init(sbase + kOffBar + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  cta_body<NT>(p, sbase, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+}
+
+}  // namespace leaf2
+
+namespace m4b {
+
+namespace {
+constexpr int kThreads = 256;
+}
+
+// The tall tile only pays when its 4096 rows are (nearly) all real rows: rows past m are zero-filled by the
+// TMA unit and looked up like any other.  Everything else stays on the 1024-row leaf.
+bool leaf2_suits(int m, int l, int n) {
+  if (m < leaf2::kTM || l <= 0 || n <= 0) return false;
+  long long const padded = ((long long)m + leaf2::kTM - 1) / leaf2::kTM * leaf2::kTM;
+  return padded * 16 <= (long long)m * 17;            // at most 1/16 of the lookups wasted on padding rows
+}
+
+// C ^= A*B for `count` (<= 7) products of identical shape in one persistent launch.
+void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *B, cudaStream_t stream) {
+  using namespace leaf2;
+  static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
+  auto kern = m4rm_leaf2_kernel<kThreads>;
+  int dev = 0;
+  M4B_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    M4B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured[dev & 63] = true;
+  }
+  if (count > kMaxBatch) die("m4ri_b200: batch of %d leaf products exceeds %d\n", count, kMaxBatch);
+  Args p;
+  p.m = A[0].nrows;
+  p.nwordsC = (Cv[0].ncols + 63) / 64;
+  p.tiles_m = (A[0].nrows + kTM - 1) / kTM;
+  p.tiles_n = (B[0].ncols + kTileBits - 1) / kTileBits;
+  p.slabs = (A[0].ncols + kSlabBits - 1) / kSlabBits;
+  p.nprob = count;
+  p.units_per_problem = (long long)p.tiles_m * p.tiles_n * p.slabs;
+  p.total_units = p.units_per_problem * count;
+  for (int i = 0; i < count; ++i) {
+    if (A[i].nrows != A[0].nrows || A[i].ncols != A[0].ncols || B[i].ncols != B[0].ncols)
+      die("m4ri_b200: batched leaf needs identical shapes\n");
+    p.C[i] = reinterpret_cast<unsigned long long *>(Cv[i].data);
+    p.pitchC[i] = Cv[i].pitch;
+    p.mapA[i] = make_map(A[i], 4, kABoxRows);
+    p.mapB[i] = make_map(B[i], 32, 8);
+  }
+  long long grid = m4rm_num_sms();
+  if (grid > p.total_units) grid = p.total_units;
+  kern<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(p);
+  M4B_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+
+}  // namespace m4b

@@ -1,0 +1,37 @@
+"""CPU check of the tall-tile M4RM leaf (m4ri_b200/csrc/m4rm_leaf2_body.h): the kernel body is compiled
+with g++ into tests/c/emu_leaf2.cpp, where a CTA is 256 host threads and TMA / mbarriers / shared
+memory are emulated, and its result is compared with a definition-level GF(2) product.  No GPU needed;
+the device build of the same source is covered by tests/test_zz_leaf2_gpu.py."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("emu") / "emu_leaf2")
+    subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-Wno-unknown-pragmas",
+                           "-I", os.path.join(ROOT, "m4ri_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "c", "emu_leaf2.cpp"), "-o", exe])
+    return exe
+
+
+def test_builtin_cases_bit_exact(emu):
+    out = subprocess.run([emu], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "FAIL" not in out.stdout and out.stdout.count("ok  ") >= 10, out.stdout
+
+
+@pytest.mark.parametrize("count,m,l,n,blocks", [
+    (1, 1, 1, 1, 1),                 # the smallest product
+    (1, 4097, 129, 257, 2),          # one past every tile / slab / word edge
+    (2, 300, 2000, 100, 9),          # long K, short and narrow C
+    (1, 12288, 256, 256, 5),         # three row tiles
+])
+def test_extra_shapes(emu, count, m, l, n, blocks):
+    out = subprocess.run([emu, str(count), str(m), str(l), str(n), str(blocks)], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0 and "FAIL" not in out.stdout, out.stdout + out.stderr
