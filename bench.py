@@ -355,7 +355,14 @@ def run_own_arm(args):
     # shared-memory roofline.  ALGORITHMIC shared-memory bytes per step of
     # 16 A-columns on a 1024x1024 C tile: 1024 rows x 2 table-row lookups x 128 B + 512 table entries
     # x 128 B written + the A (1024 x 2 B) and B (16 x 128 B) slab reads = 331776 B per 2*16*1024*1024 bit-ops.
-    smem_bytes_per_bitop = (1024 * 2 * 128 + 512 * 128 + 1024 * 2 + 16 * 128) / (2.0 * 16 * 1024 * 1024)
+    # The tall-tile leaf (variant 2, m4rm_leaf2.cu) per step of 32 A-columns on a 4096 x 256-bit tile: 4096 rows x 8
+    # 16-byte lookups + 2048 16-byte table pieces written + A (4096 x 4 B) and B (32 x 32 B) = 574464 B per
+    # 2*32*4096*256 bit-ops.
+    leaf_variant = lib.m4ri_b200_last_leaf_variant()
+    if leaf_variant == 2:
+        smem_bytes_per_bitop = (4096 * 8 * 16 + 2048 * 16 + 4096 * 4 + 32 * 32) / (2.0 * 32 * 4096 * 256)
+    else:
+        smem_bytes_per_bitop = (1024 * 2 * 128 + 512 * 128 + 1024 * 2 + 16 * 128) / (2.0 * 16 * 1024 * 1024)
     smem_peak_gbs = 128.0 * 148 * sm_max_mhz * 1e6 / 1e9
     smem_achieved_gbs = leaf_rate * smem_bytes_per_bitop / 1e9
     leaf_dims = None
@@ -379,11 +386,12 @@ def run_own_arm(args):
     tpath = os.path.join(ROOT, "profiles", "leaf_traffic.json")
     if os.path.exists(tpath) and leaf_dims:
         with open(tpath) as f:
-            traffic = json.load(f).get("x".join(str(d) for d in leaf_dims))
+            traffic = json.load(f).get(("leaf2:" if leaf_variant == 2 else "") + "x".join(str(d) for d in leaf_dims))
         if traffic is not None:
             traffic *= products_per_launch
     roofline = {
-        "kernel": "m4rm_streamk_kernel", "bound": "smem", "unit": "GB/s",
+        "kernel": "m4rm_leaf2_kernel" if leaf_variant == 2 else "m4rm_streamk_kernel", "bound": "smem", "unit": "GB/s",
+        "algorithmic_smem_bytes_per_bitop": smem_bytes_per_bitop,
         "achieved": smem_achieved_gbs, "peak": smem_peak_gbs, "frac": smem_achieved_gbs / smem_peak_gbs,
         "peak_source": f"128 B/clk/SM x 148 SMs x {sm_max_mhz:.0f} MHz (clocks.max.sm, {peak_src})",
         "traffic": traffic,

@@ -78,6 +78,7 @@ def _declare(lib):
     lib.m4ri_b200_get_default_cutoff.restype = c_int
     lib.m4ri_b200_last_path.restype = c_char_p
     lib.m4ri_b200_set_leaf_variant.argtypes, lib.m4ri_b200_set_leaf_variant.restype = [c_int], c_int
+    lib.m4ri_b200_last_leaf_variant.restype = c_int
     lib.m4ri_b200_kernel_launches.restype = c_uint64
     lib.m4ri_b200_profile_end.argtypes = [POINTER(ctypes.c_double), POINTER(ctypes.c_double)]
     lib.m4ri_b200_profile_end.restype = c_uint64

@@ -505,6 +505,8 @@ int m4ri_b200_set_leaf_variant(int variant) {
   return prev;
 }
 
+int m4ri_b200_last_leaf_variant(void) { return g_last_leaf; }
+
 char const *m4ri_b200_last_path(void) { return g.last_path; }
 uint64_t    m4ri_b200_kernel_launches(void) { return g_kernel_launches; }
 

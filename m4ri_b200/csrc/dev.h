@@ -52,6 +52,7 @@ bool leaf2_suits(int m, int l, int n);
 void launch_m4rm_leaf2(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream);
 // 0 = automatic (leaf2 where it suits), 1 = always the 1024-row leaf, 2 = leaf2 whenever m >= 1
 extern int g_leaf_variant;
+extern int g_last_leaf;
 void leaf_profile_begin();
 unsigned long long leaf_profile_end(double *ms, double *bitops);
 

@@ -435,6 +435,7 @@ int m4rm_num_sms() {
 
 // Leaf selection: M4RI_B200_LEAF=0|1|2 in the environment, or m4ri_b200_set_leaf_variant() at run time.
 int g_leaf_variant = -1;
+int g_last_leaf = 0;        // kernel of the most recent leaf launch: 1 = 1024 x 1024-bit tiles, 2 = 4096 x 256-bit tiles
 static int leaf_variant() {
   if (g_leaf_variant < 0) {
     char const *env = getenv("M4RI_B200_LEAF");
@@ -459,7 +460,9 @@ static void launch_leaf(int count, DView const *C, DView const *A, DView const *
     M4B_CUDA(cudaEventRecord(ev->first, stream));
   }
   int const variant = leaf_variant();
-  if (!overwrite && (variant == 2 || (variant == 0 && leaf2_suits(A[0].nrows, A[0].ncols, B[0].ncols))))
+  bool const tall = !overwrite && (variant == 2 || (variant == 0 && leaf2_suits(A[0].nrows, A[0].ncols, B[0].ncols)));
+  g_last_leaf = tall ? 2 : 1;
+  if (tall)
     launch_m4rm_leaf2(count, C, A, B, stream);                       // tall tiles: 4096 rows x 256 bits
   else if (A[0].nrows <= 256)
     launch_variant<256, 256>(count, C, A, B, overwrite, stream);     // short operands: 256-row tiles

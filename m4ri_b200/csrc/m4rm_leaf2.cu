@@ -79,7 +79,7 @@ L2_FN void warp_sync() { __syncwarp(); }
 
 namespace leaf2 {
 
-template <int NT>
+template <int NT, int AWIDE>
 __global__ void __launch_bounds__(NT, 1) m4rm_leaf2_kernel(const __grid_constant__ Args p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint32_t const sbase = smem_u32(smem);
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NT, 1) m4rm_leaf2_kernel(const __grid_constant
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  cta_body<NT>(p, sbase, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+  cta_body<NT, AWIDE>(p, sbase, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 }  // namespace leaf2
@@ -112,8 +112,13 @@ bool leaf2_suits(int m, int l, int n) {
 // C ^= A*B for `count` (<= 7) products of identical shape in one persistent launch.
 void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *B, cudaStream_t stream) {
   using namespace leaf2;
+  // experiment knob: M4RI_B200_LEAF2_AWIDE=1 loads the A bits of a whole slab per row with one LDS.128
+  static int const awide = [] {
+    char const *env = getenv("M4RI_B200_LEAF2_AWIDE");
+    return env && env[0] == '1' ? 1 : 0;
+  }();
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
-  auto kern = m4rm_leaf2_kernel<kThreads>;
+  auto kern = awide ? m4rm_leaf2_kernel<kThreads, 1> : m4rm_leaf2_kernel<kThreads, 0>;
   int dev = 0;
   M4B_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {

@@ -134,7 +134,7 @@ L2_FN void lookup_row(U4 &acc0, U4 &acc1, uint32_t a, uint32_t const (&base)[4])
 
 // The persistent stream-K CTA.  sbase = shared-memory address of the dynamic segment (1024-byte aligned),
 // mbarriers at sbase + kOffBar already initialised (count 1) and visible to all threads.
-template <int NT>
+template <int NT, int AWIDE>
 L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks) {
   constexpr int RT = kTM / NT;                      // rows per thread, each as two 16-byte pieces
   uint32_t const sTab = sbase + kOffTables;
@@ -197,17 +197,13 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
     for (int i = 0; i < nseg; ++i) {
       uint32_t const slot = (uint32_t)i & 1u;
       uint32_t const bS = sB + slot * kBSlabBytes;
-      auto half = [&](auto H_) {
-        constexpr int H = decltype(H_)::value;
-        // the thread's A bits of two steps, one u32 per row and step, bytes rotated by the lane's table phase
-        // (an LDS.128 per row and slab would halve these wavefronts but needs 32 more live registers)
-        uint32_t aw[RT][2];
-#pragma unroll
-        for (int j = 0; j < RT; ++j) {
-          U2 const r = lds64(sA + slot * kASlabBytes + (uint32_t)(j * NT + tid) * 16u + H * 8u);
-          aw[j][0] = prmt(r.x, 0u, rot);
-          aw[j][1] = prmt(r.y, 0u, rot);
-        }
+      // A bits of SP steps per load: one u32 per row and step, bytes rotated by the lane's table phase.
+      // AWIDE = 0: an LDS.64 per row and half slab (4 wavefronts per 32 rows for 2 steps);
+      // AWIDE = 1: an LDS.128 per row and slab (4 wavefronts for 4 steps, but 32 more live registers).
+      constexpr int SP = AWIDE ? 4 : 2;
+      auto part = [&](auto P_) {
+        constexpr int P = decltype(P_)::value;
+        uint32_t aw[RT][SP];
         auto step = [&](auto S_) {
           constexpr int S = decltype(S_)::value;          // step within the slab; table buffer = S & 1
           uint32_t const tnext = sTab + ((S & 1) ^ 1) * kStepBufBytes;
@@ -219,16 +215,39 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
             else           { mbar_wait(sBar, parity0);     parity0 ^= 1; }
             build_tables<NT>(tnext, sB + (slot ^ 1u) * kBSlabBytes, tid);
           }
+          // ---- A bits of the next SP steps (after the build: its registers are dead by now) ----
+          if constexpr (S % SP == 0) {
+#pragma unroll
+          for (int j = 0; j < RT; ++j) {
+            uint32_t const arow = sA + slot * kASlabBytes + (uint32_t)(j * NT + tid) * 16u;
+            if constexpr (AWIDE) {
+              U4 const r = lds128(arow);
+              aw[j][0] = prmt(r.x, 0u, rot);
+              aw[j][1] = prmt(r.y, 0u, rot);
+              aw[j][2] = prmt(r.z, 0u, rot);
+              aw[j][3] = prmt(r.w, 0u, rot);
+            } else {
+              U2 const r = lds64(arow + P * 8u);
+              aw[j][0] = prmt(r.x, 0u, rot);
+              aw[j][1] = prmt(r.y, 0u, rot);
+            }
+          }
+          }
           // ---- lookups (rows past m carry zero-filled A bits -> line 0 = zeros; no branch needed) ----
 #pragma unroll
-          for (int j = 0; j < RT; ++j) lookup_row<(S & 1) * kStepBufBytes>(acc[j][0], acc[j][1], aw[j][S & 1], base);
+          for (int j = 0; j < RT; ++j)
+            lookup_row<(S & 1) * kStepBufBytes>(acc[j][0], acc[j][1], aw[j][S % SP], base);
           cta_sync();
         };
-        step(IntC<2 * H>{});
-        step(IntC<2 * H + 1>{});
+        step(IntC<SP * P>{});
+        step(IntC<SP * P + 1>{});
+        if constexpr (SP == 4) {
+          step(IntC<SP * P + 2>{});
+          step(IntC<SP * P + 3>{});
+        }
       };
-      half(IntC<0>{});
-      half(IntC<1>{});
+      part(IntC<0>{});
+      if constexpr (SP == 2) part(IntC<1>{});
       // ring slot `slot` is free again: refill it with slab i+2
       if (warp == 0 && i + 2 < nseg) issue(i + 2);
     }

@@ -25,6 +25,9 @@
 #include <vector>
 
 #define L2_FN inline
+#ifndef EMU_AWIDE
+#define EMU_AWIDE 0   // which A-load variant of the kernel body to emulate
+#endif
 
 namespace leaf2 {
 
@@ -239,7 +242,7 @@ bool run_case(int count, int m, int l, int n, int nblocks) {
           }
         }
         cta_sync();
-        cta_body<kEmuThreads>(p, kEmuSbase, tid, bid, nblocks);
+        cta_body<kEmuThreads, EMU_AWIDE>(p, kEmuSbase, tid, bid, nblocks);
         cta_sync();
       }
     });
