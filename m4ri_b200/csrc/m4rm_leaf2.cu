@@ -71,7 +71,11 @@ L2_FN void red_xor64(unsigned long long *p, uint32_t lo, uint32_t hi) {
   asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 L2_FN void cta_sync() { __syncthreads(); }
-L2_FN void warp_sync() { __syncwarp(); }
+L2_FN uint32_t gate(uint32_t a, uint32_t b, uint32_t c) {   // a | (b & c) as ONE LOP3 the compiler cannot see through
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xF8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
 
 }  // namespace leaf2
 
@@ -135,6 +139,8 @@ void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *
   p.nprob = count;
   p.units_per_problem = (long long)p.tiles_m * p.tiles_n * p.slabs;
   p.total_units = p.units_per_problem * count;
+  p.zero = 0;
+  if (p.total_units >= (1ll << 31)) die("m4ri_b200: leaf product too large for 32-bit unit counters\n");
   for (int i = 0; i < count; ++i) {
     if (A[i].nrows != A[0].nrows || A[i].ncols != A[0].ncols || B[i].ncols != B[0].ncols)
       die("m4ri_b200: batched leaf needs identical shapes\n");

@@ -18,7 +18,7 @@
 // where a CTA is 256 host threads, shared memory an array, TMA a host copy and the mbarriers/atomics are
 // emulated — so the index arithmetic of this file is tested on the CPU (tests/test_leaf2_emu.py) without
 // being restated.  The includer provides: L2_FN, U4, U2, TMap, lds128, lds64, sts128, prmt, mbar_wait,
-// mbar_expect_tx, tma_load_2d, red_xor64, cta_sync, warp_sync; lds128 also as lds128<IMM>(addr) = [addr + IMM].
+// mbar_expect_tx, tma_load_2d, red_xor64, cta_sync, gate(a, b, c) = a | (b & c); lds128 also as lds128<IMM>(addr) = [addr + IMM].
 #pragma once
 #include <stdint.h>
 
@@ -44,6 +44,7 @@ constexpr int kOffTables    = 0;
 constexpr int kOffA         = 2 * kStepBufBytes;
 constexpr int kOffB         = kOffA + 2 * kASlabBytes;
 constexpr int kOffBar       = kOffB + 2 * kBSlabBytes;
+constexpr int kOffSeg       = kOffBar + 16;               // {prob, tn, row0, s0} of the current segment
 constexpr int kSmemBytes    = kOffBar + 64;               // 229 440 B  (limit 232 448)
 constexpr uint32_t kSlabTxBytes = kASlabBytes + kBSlabBytes;
 constexpr int kMaxBatch     = 7;
@@ -60,7 +61,8 @@ struct alignas(64) Args {
   int slabs;                     // ceil(l / 128)
   int nprob;
   long long units_per_problem;   // tiles_m * tiles_n * slabs
-  long long total_units;
+  long long total_units;         // < 2^31
+  unsigned zero;                 // 0 — a value the compiler cannot know (see gate())
 };
 
 template <int N>
@@ -118,8 +120,15 @@ L2_FN void build_tables(uint32_t tbuf, uint32_t bstep, int tid) {
 // its bytes already rotated by the lane's table phase, so byte jj indexes table (i8 + jj) & 3 — the table
 // whose piece this lane reads in its jj-th load (base[jj] = lane part of the address, IMM = table buffer).
 // acc0 is the lane's "own" half (hl), acc1 the other one.
+// `dep` chains the rows of a thread: the A word of a row is OR-ed with (dep & zero) — still the A word, but
+// now data dependent on the last table line of the previous row — so a warp never has more than one row's
+// eight LDS.128 (32 registers) in flight.  Without the chain ptxas schedules for single-warp latency, keeps
+// ~12 loads in flight and spills accumulators to make room; with 224 KB of shared memory there is hardly
+// any L1 left, so every spilled word costs an L2 round trip.  Eight warps x 8 loads still oversubscribe
+// the data pipe (one LDS.128 per 4 clocks) several times.
 template <int IMM>
-L2_FN void lookup_row(U4 &acc0, U4 &acc1, uint32_t a, uint32_t const (&base)[4]) {
+L2_FN void lookup_row(U4 &acc0, U4 &acc1, uint32_t a, uint32_t const (&base)[4], uint32_t &dep, uint32_t zero) {
+  a = gate(a, dep, zero);
   uint32_t ad[4];
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) ad[jj] = base[jj] + prmt(a, 0u, 0x4440u + jj) * kLineBytes;
@@ -130,10 +139,41 @@ L2_FN void lookup_row(U4 &acc0, U4 &acc1, uint32_t a, uint32_t const (&base)[4])
            w3 = lds128<IMM>(ad[3] ^ 64u);
   xor4(acc1, w0, w1);
   xor4(acc1, w2, w3);
+  // every word of this row's sixteen table pieces feeds dep, so none of them can stay unconsumed
+  dep = (acc0.x ^ acc0.y ^ acc0.z) ^ (acc0.w ^ acc1.x ^ acc1.y) ^ (acc1.z ^ acc1.w);
+}
+
+// TMA for K-slab `kslab` of the current segment into ring slot `slot`: 16 boxes of A (256 rows x 16 B) and
+// 16 boxes of B (one per table: 8 rows x 128 B, see kBBoxBytes).  TMA instructions are issued one thread
+// at a time, so the 32 of a slab are spread over the warps (lanes 0-3 of warp w take operations 4w .. 4w+3):
+// no warp falls more than four issue slots behind the others at the next barrier.  complete_tx may overtake
+// thread 0's arrive.expect_tx — the phase cannot complete before that arrival, the tx-count is signed.
+template <int NT>
+L2_FN void issue_slab(Args const &p, uint32_t sbase, int tid, int prob, int tn, int row0, int kslab, uint32_t slot) {
+  uint32_t const bar = sbase + kOffBar + 8u * slot;
+  if (tid == 0) mbar_expect_tx(bar, kSlabTxBytes);
+  constexpr int kOpsPerWarp = 32 / (NT / 32);
+  int const lane = tid & 31;
+  if (lane < kOpsPerWarp) {
+    int const op = (tid >> 5) * kOpsPerWarp + lane;
+    if (op < kAParts)
+      tma_load_2d(sbase + kOffA + slot * kASlabBytes + op * (kABoxRows * 16), &p.mapA[prob], kslab * 4,
+                  row0 + op * kABoxRows, bar);
+    else {
+      int const box = op - kAParts;                // table box & 3 of step box >> 2
+      tma_load_2d(sbase + kOffB + slot * kBSlabBytes + box * kBBoxBytes, &p.mapB[prob], tn * 8 - 8 * (box & 3),
+                  kslab * kSlabBits + box * 8, bar);
+    }
+  }
 }
 
 // The persistent stream-K CTA.  sbase = shared-memory address of the dynamic segment (1024-byte aligned),
 // mbarriers at sbase + kOffBar already initialised (count 1) and visible to all threads.
+//
+// Register budget: 128 registers of C and 32 of A bits leave little room, and a spilled value costs an L2
+// round trip here (the 224 KB of shared memory leave almost no L1), so the per-segment scalars live in
+// shared memory (kOffSeg) and the ring state is ONE counter: K-slab number n of this CTA uses ring slot
+// n & 1 and mbarrier phase parity (n >> 1) & 1.
 template <int NT, int AWIDE>
 L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks) {
   constexpr int RT = kTM / NT;                      // rows per thread, each as two 16-byte pieces
@@ -141,8 +181,8 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
   uint32_t const sA   = sbase + kOffA;
   uint32_t const sB   = sbase + kOffB;
   uint32_t const sBar = sbase + kOffBar;
-  int const warp = tid >> 5, lane = tid & 31;
-  int const i8 = lane & 7, hl = i8 >> 2;
+  uint32_t const sSeg = sbase + kOffSeg;
+  int const i8 = tid & 7, hl = i8 >> 2;
 
   // lane constants: byte rotation of the A words (table phase) and the lane part of the lookup addresses
   uint32_t const rot = ((uint32_t)(i8 + 0) & 3u) | (((uint32_t)(i8 + 1) & 3u) << 4) | (((uint32_t)(i8 + 2) & 3u) << 8) |
@@ -151,51 +191,35 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) base[jj] = sTab + (uint32_t)hl * 64u + ((uint32_t)(i8 + jj) & 3u) * 16u;
 
-  long long const u_begin = p.total_units * (long long)bid / nblocks;
-  long long const u_end   = p.total_units * (long long)(bid + 1) / nblocks;
-  uint32_t parity0 = 0, parity1 = 0;                // phase of each ring slot
+  int const total = (int)p.total_units, upp = (int)p.units_per_problem;      // < 2^31, checked by the launcher
+  int u = (int)((long long)total * bid / nblocks);
+  int const u_end = (int)((long long)total * (bid + 1) / nblocks);
+  uint32_t ring = 0;                                // K-slabs consumed so far by this CTA
+  uint32_t dep = 0;                                 // see lookup_row()
 
-  for (long long u = u_begin; u < u_end;) {
-    int const prob      = (int)(u / p.units_per_problem);
-    long long const v   = u - (long long)prob * p.units_per_problem;
-    int const tile      = (int)(v / p.slabs);
-    int const s0        = (int)(v % p.slabs);
-    TMap const *mapA = &p.mapA[prob], *mapB = &p.mapB[prob];
-    int nseg            = p.slabs - s0;
-    if ((long long)nseg > u_end - u) nseg = (int)(u_end - u);
-    int const tm = tile % p.tiles_m, tn = tile / p.tiles_m;
-    int const row0 = tm * kTM;
-
-    // warp 0: TMA for slab s0+i into ring slot i&1 — lane 0 arms the barrier, lanes 0..15 each fetch one
-    // A box (256 rows) and one B box (table lane&3 of step lane>>2)
-    auto issue = [&](int i) {
-      uint32_t const slot = (uint32_t)i & 1u;
-      uint32_t const bar  = sBar + 8u * slot;
-      if (lane == 0) mbar_expect_tx(bar, kSlabTxBytes);
-      warp_sync();
-      if (lane < kAParts) {
-        tma_load_2d(sA + slot * kASlabBytes + lane * (kABoxRows * 16), mapA, (s0 + i) * 4, row0 + lane * kABoxRows, bar);
-        tma_load_2d(sB + slot * kBSlabBytes + lane * kBBoxBytes, mapB, tn * 8 - 8 * (lane & 3),
-                    (s0 + i) * kSlabBits + lane * 8, bar);
-      }
-    };
-
-    if (warp == 0) {
-      issue(0);
-      if (nseg > 1) issue(1);
+  while (u < u_end) {
+    int nseg;
+    {
+      int const prob = u / upp, v = u - prob * upp;
+      int const tile = v / p.slabs, s0 = v - tile * p.slabs;
+      int const tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+      nseg = p.slabs - s0;
+      if (nseg > u_end - u) nseg = u_end - u;
+      if (tid == 0) sts128(sSeg, U4{(uint32_t)prob, (uint32_t)tn, (uint32_t)(tm * kTM), (uint32_t)s0});
+      issue_slab<NT>(p, sbase, tid, prob, tn, tm * kTM, s0, ring & 1u);
+      if (nseg > 1) issue_slab<NT>(p, sbase, tid, prob, tn, tm * kTM, s0 + 1, (ring + 1u) & 1u);
     }
 
     U4 acc[RT][2];
 #pragma unroll
     for (int j = 0; j < RT; ++j) acc[j][0] = acc[j][1] = U4{0u, 0u, 0u, 0u};
 
-    mbar_wait(sBar, parity0);
-    parity0 ^= 1;
-    build_tables<NT>(sTab, sB, tid);
+    mbar_wait(sBar + 8u * (ring & 1u), (ring >> 1) & 1u);
+    build_tables<NT>(sTab, sB + (ring & 1u) * kBSlabBytes, tid);
     cta_sync();
 
     for (int i = 0; i < nseg; ++i) {
-      uint32_t const slot = (uint32_t)i & 1u;
+      uint32_t const n = ring + (uint32_t)i, slot = n & 1u;
       uint32_t const bS = sB + slot * kBSlabBytes;
       // A bits of SP steps per load: one u32 per row and step, bytes rotated by the lane's table phase.
       // AWIDE = 0: an LDS.64 per row and half slab (4 wavefronts per 32 rows for 2 steps);
@@ -211,32 +235,31 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
           if constexpr (S < kStepsPerSlab - 1) {
             build_tables<NT>(tnext, bS + (S + 1) * 4 * kBBoxBytes, tid);
           } else if (i + 1 < nseg) {
-            if (slot == 0) { mbar_wait(sBar + 8, parity1); parity1 ^= 1; }
-            else           { mbar_wait(sBar, parity0);     parity0 ^= 1; }
+            mbar_wait(sBar + 8u * (slot ^ 1u), ((n + 1u) >> 1) & 1u);
             build_tables<NT>(tnext, sB + (slot ^ 1u) * kBSlabBytes, tid);
           }
           // ---- A bits of the next SP steps (after the build: its registers are dead by now) ----
           if constexpr (S % SP == 0) {
 #pragma unroll
-          for (int j = 0; j < RT; ++j) {
-            uint32_t const arow = sA + slot * kASlabBytes + (uint32_t)(j * NT + tid) * 16u;
-            if constexpr (AWIDE) {
-              U4 const r = lds128(arow);
-              aw[j][0] = prmt(r.x, 0u, rot);
-              aw[j][1] = prmt(r.y, 0u, rot);
-              aw[j][2] = prmt(r.z, 0u, rot);
-              aw[j][3] = prmt(r.w, 0u, rot);
-            } else {
-              U2 const r = lds64(arow + P * 8u);
-              aw[j][0] = prmt(r.x, 0u, rot);
-              aw[j][1] = prmt(r.y, 0u, rot);
+            for (int j = 0; j < RT; ++j) {
+              uint32_t const arow = sA + slot * kASlabBytes + (uint32_t)(j * NT + tid) * 16u;
+              if constexpr (AWIDE) {
+                U4 const r = lds128(arow);
+                aw[j][0] = prmt(r.x, 0u, rot);
+                aw[j][1] = prmt(r.y, 0u, rot);
+                aw[j][2] = prmt(r.z, 0u, rot);
+                aw[j][3] = prmt(r.w, 0u, rot);
+              } else {
+                U2 const r = lds64(arow + P * 8u);
+                aw[j][0] = prmt(r.x, 0u, rot);
+                aw[j][1] = prmt(r.y, 0u, rot);
+              }
             }
-          }
           }
           // ---- lookups (rows past m carry zero-filled A bits -> line 0 = zeros; no branch needed) ----
 #pragma unroll
           for (int j = 0; j < RT; ++j)
-            lookup_row<(S & 1) * kStepBufBytes>(acc[j][0], acc[j][1], aw[j][S % SP], base);
+            lookup_row<(S & 1) * kStepBufBytes>(acc[j][0], acc[j][1], aw[j][S % SP], base, dep, p.zero);
           cta_sync();
         };
         step(IntC<SP * P>{});
@@ -248,26 +271,34 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
       };
       part(IntC<0>{});
       if constexpr (SP == 2) part(IntC<1>{});
-      // ring slot `slot` is free again: refill it with slab i+2
-      if (warp == 0 && i + 2 < nseg) issue(i + 2);
+      // ring slot `slot` is free again: refill it with slab i+2 of the segment
+      if (i + 2 < nseg) {
+        U4 const seg = lds128(sSeg);
+        issue_slab<NT>(p, sbase, tid, (int)seg.x, (int)seg.y, (int)seg.z, (int)seg.w + i + 2, slot);
+      }
     }
 
     // ---- merge the partial tile into C (exact: XOR is associative and commutative) ----
+    {
+      U4 const seg = lds128(sSeg);
+      int const prob = (int)seg.x, tn = (int)seg.y, row0 = (int)seg.z;
 #pragma unroll
-    for (int j = 0; j < RT; ++j) {
-      int const row = row0 + j * NT + tid;
-      if (row < p.m) {
+      for (int j = 0; j < RT; ++j) {
+        int const row = row0 + j * NT + tid;
+        if (row < p.m) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          int const wcol = tn * (kTileBits / 64) + (hl ^ hh) * 2;
-          unsigned long long *dst = p.C[prob] + (long long)row * p.pitchC[prob] + wcol;
-          if (wcol < p.nwordsC) red_xor64(dst, acc[j][hh].x, acc[j][hh].y);
-          if (wcol + 1 < p.nwordsC) red_xor64(dst + 1, acc[j][hh].z, acc[j][hh].w);
+          for (int hh = 0; hh < 2; ++hh) {
+            int const wcol = tn * (kTileBits / 64) + (hl ^ hh) * 2;
+            unsigned long long *dst = p.C[prob] + (long long)row * p.pitchC[prob] + wcol;
+            if (wcol < p.nwordsC) red_xor64(dst, acc[j][hh].x, acc[j][hh].y);
+            if (wcol + 1 < p.nwordsC) red_xor64(dst + 1, acc[j][hh].z, acc[j][hh].w);
+          }
         }
       }
     }
-    // all table/slab reads of this segment are complete before the next segment's prologue
+    // all table/slab/segment reads of this segment are complete before the next segment's prologue
     cta_sync();
+    ring += (uint32_t)nseg;
     u += nseg;
   }
 }

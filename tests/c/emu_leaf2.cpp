@@ -48,7 +48,6 @@ constexpr int kEmuThreads = 256;
 constexpr uint32_t kEmuSbase = 1024;          // dynamic shared memory starts 1024-byte aligned, not at 0
 static uint8_t g_smem[kEmuSbase + 232448];
 static std::barrier<> g_cta_barrier(kEmuThreads);
-static std::unique_ptr<std::barrier<>> g_warp_barrier[kEmuThreads / 32];
 struct EmuMbar {
   std::atomic<long> tx{0};
   std::atomic<int> pending{1};
@@ -56,7 +55,6 @@ struct EmuMbar {
 };
 static EmuMbar g_bar[2];
 static uint32_t g_bar_base = 0;
-static thread_local int t_tid = 0;
 
 static std::atomic<long> g_n_lds128{0}, g_n_sts128{0};
 
@@ -150,7 +148,7 @@ L2_FN void red_xor64(unsigned long long *p, uint32_t lo, uint32_t hi) {
   __atomic_fetch_xor(p, ((unsigned long long)hi << 32) | lo, __ATOMIC_RELAXED);
 }
 L2_FN void cta_sync() { g_cta_barrier.arrive_and_wait(); }
-L2_FN void warp_sync() { g_warp_barrier[t_tid >> 5]->arrive_and_wait(); }
+L2_FN uint32_t gate(uint32_t a, uint32_t b, uint32_t c) { return a | (b & c); }
 
 }  // namespace leaf2
 
@@ -231,7 +229,6 @@ bool run_case(int count, int m, int l, int n, int nblocks) {
   std::vector<std::thread> th;
   for (int tid = 0; tid < kEmuThreads; ++tid)
     th.emplace_back([&, tid] {
-      t_tid = tid;
       for (int bid = 0; bid < nblocks; ++bid) {
         if (tid == 0) {                 // a fresh CTA: garbage shared memory, freshly initialised mbarriers
           for (size_t i = 0; i < sizeof g_smem; ++i) g_smem[i] = (uint8_t)(0xA5 ^ i);
@@ -289,7 +286,6 @@ bool check_bank_groups() {
 }  // namespace
 
 int main(int argc, char **argv) {
-  for (auto &w : leaf2::g_warp_barrier) w = std::make_unique<std::barrier<>>(32);
   static_assert(leaf2::kSmemBytes <= 232448, "shared memory budget");
   bool ok = check_bank_groups();
   if (argc == 6) {
