@@ -70,6 +70,22 @@ CUtensorMap make_map(DView V, int box_w32, int box_rows) {
   return map;
 }
 
+CUtensorMap make_map_row_groups(DView V, int box_w32, int group_rows, int box_groups) {
+  if (V.nrows % group_rows) die("m4ri_b200: make_map_row_groups needs nrows %% %d == 0\n", group_rows);
+  CUtensorMap map;
+  cuuint64_t dims[3]    = {(cuuint64_t)((V.ncols + 127) / 128) * 4, (cuuint64_t)group_rows, (cuuint64_t)(V.nrows / group_rows)};
+  cuuint64_t strides[2] = {(cuuint64_t)V.pitch * 8, (cuuint64_t)V.pitch * 8 * group_rows};
+  cuuint32_t box[3]     = {(cuuint32_t)box_w32, (cuuint32_t)group_rows, (cuuint32_t)box_groups};
+  cuuint32_t estr[3]    = {1, 1, 1};
+  CUresult r = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, V.data, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    die("m4ri_b200: cuTensorMapEncodeTiled (3D) failed (%d) for view %p pitch %lld %dx%d\n", (int)r, (void *)V.data,
+        (long long)V.pitch, V.nrows, V.ncols);
+  return map;
+}
+
 namespace {
 
 constexpr int kTileBits   = 1024;               // C tile width in bits (one table row = 128 B)

@@ -2,8 +2,8 @@
 //
 // The body header is written against a handful of primitives so that the same source also runs inside
 // the CPU emulation harness tests/c/emu_leaf2.cpp; here they are the sm_100a instructions themselves:
-// LDS.128 / STS.128, PRMT, mbarrier try_wait / arrive.expect_tx, cp.async.bulk.tensor.2d (TMA),
-// red.global.xor.b64.
+// LDS.128 / STS.128, PRMT, mbarrier try_wait / arrive.expect_tx, cp.async.bulk.tensor.2d/.3d (TMA),
+// cp.async (LDGSTS), red.global.xor.b64.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -66,6 +66,17 @@ L2_FN void tma_load_2d(uint32_t dst, TMap const *map, int c0, int c1, uint32_t b
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+L2_FN void tma_load_3d(uint32_t dst, TMap const *map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+// LDGSTS: 16 bytes global -> shared without a register round trip; src_bytes = 0 writes zeros
+L2_FN void cp_async16(uint32_t dst, void const *src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+L2_FN void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 L2_FN void red_xor64(unsigned long long *p, uint32_t lo, uint32_t hi) {
   unsigned long long v = (static_cast<unsigned long long>(hi) << 32) | lo;
   asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -132,6 +143,8 @@ void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *
   if (count > kMaxBatch) die("m4ri_b200: batch of %d leaf products exceeds %d\n", count, kMaxBatch);
   Args p;
   p.m = A[0].nrows;
+  p.l = B[0].nrows;
+  p.a3d = A[0].nrows % kABoxRows == 0 ? 1 : 0;
   p.nwordsC = (Cv[0].ncols + 63) / 64;
   p.tiles_m = (A[0].nrows + kTM - 1) / kTM;
   p.tiles_n = (B[0].ncols + kTileBits - 1) / kTileBits;
@@ -146,8 +159,9 @@ void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *
       die("m4ri_b200: batched leaf needs identical shapes\n");
     p.C[i] = reinterpret_cast<unsigned long long *>(Cv[i].data);
     p.pitchC[i] = Cv[i].pitch;
-    p.mapA[i] = make_map(A[i], 4, kABoxRows);
-    p.mapB[i] = make_map(B[i], 32, 8);
+    p.mapA[i] = p.a3d ? make_map_row_groups(A[i], 4, kABoxRows, kAParts) : make_map(A[i], 4, kABoxRows);
+    p.B[i] = reinterpret_cast<unsigned long long const *>(B[i].data);
+    p.pitchB[i] = B[i].pitch;
   }
   long long grid = m4rm_num_sms();
   if (grid > p.total_units) grid = p.total_units;

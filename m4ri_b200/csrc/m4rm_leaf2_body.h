@@ -18,7 +18,7 @@
 // where a CTA is 256 host threads, shared memory an array, TMA a host copy and the mbarriers/atomics are
 // emulated — so the index arithmetic of this file is tested on the CPU (tests/test_leaf2_emu.py) without
 // being restated.  The includer provides: L2_FN, U4, U2, TMap, lds128, lds64, sts128, prmt, mbar_wait,
-// mbar_expect_tx, tma_load_2d, red_xor64, cta_sync, gate(a, b, c) = a | (b & c); lds128 also as lds128<IMM>(addr) = [addr + IMM].
+// mbar_expect_tx, tma_load_2d, tma_load_3d, cp_async16, cp_async_wait_all, red_xor64, cta_sync, gate(a, b, c) = a | (b & c); lds128 also as lds128<IMM>(addr) = [addr + IMM].
 #pragma once
 #include <stdint.h>
 
@@ -33,28 +33,32 @@ constexpr int kStepsPerSlab = kSlabBits / 32;             // 4
 constexpr int kABoxRows     = 256;
 constexpr int kAParts       = kTM / kABoxRows;            // 16 boxes of 256 rows x 16 B
 constexpr int kASlabBytes   = kTM * 16;                   // 64 KB
-// B arrives as one box per table: 8 rows x 128 B whose first column is 8*t words LEFT of the tile, so the
-// 32 wanted bytes of table t sit 32*t bytes into each 128-byte box row.  That skew is what spreads the eight
-// (t, h) pieces a quarter-warp reads over all eight 16-byte bank groups (TMA destinations must be 128-byte
-// aligned, so the boxes themselves cannot be skewed); out-of-range (also negative) columns are zero-filled.
-constexpr int kBBoxBytes    = 8 * 128;
-constexpr int kBBoxes       = kStepsPerSlab * 4;          // 16 per slab
-constexpr int kBSlabBytes   = kBBoxes * kBBoxBytes;       // 16 KB
+// B is only 4 KB per slab and CTA (128 rows x 32 B), so it does not come by TMA: every thread fetches ONE
+// 16-byte piece per slab with cp.async (LDGSTS), which can put it anywhere — straight into the layout the
+// table build wants: piece (step s, row-in-table b, half h, table t) at s*1024 + b*128 + h*64 + t*16, i.e. the
+// eight (h, t) pieces a quarter-warp reads for one b form one 128-byte line (all eight bank groups), with
+// no over-fetch and no extra TMA instructions (a TMA issue costs its warp several hundred cycles).
+constexpr int kBStepBytes   = 8 * kLineBytes;             // 1 KB
+constexpr int kBSlabBytes   = kStepsPerSlab * kBStepBytes;   // 4 KB
 constexpr int kOffTables    = 0;
 constexpr int kOffA         = 2 * kStepBufBytes;
 constexpr int kOffB         = kOffA + 2 * kASlabBytes;
 constexpr int kOffBar       = kOffB + 2 * kBSlabBytes;
 constexpr int kOffSeg       = kOffBar + 16;               // {prob, tn, row0, s0} of the current segment
-constexpr int kSmemBytes    = kOffBar + 64;               // 229 440 B  (limit 232 448)
-constexpr uint32_t kSlabTxBytes = kASlabBytes + kBSlabBytes;
+constexpr int kSmemBytes    = kOffBar + 64;               // 204 864 B  (limit 232 448)
+constexpr uint32_t kSlabTxBytes = kASlabBytes;
 constexpr int kMaxBatch     = 7;
 
 struct alignas(64) Args {
-  TMap mapA[kMaxBatch];          // box 4 x u32 (16 B) x 256 rows
-  TMap mapB[kMaxBatch];          // box 32 x u32 (128 B) x 8 rows
+  TMap mapA[kMaxBatch];          // a3d: 3D (words, 256 rows, row groups), box 4 x 256 x 16 = one slab of a tile;
+                                 // else 2D (words, rows), box 4 x 256
+  unsigned long long const *B[kMaxBatch];
+  long long pitchB[kMaxBatch];   // words (even; bits past the last column up to the pitch are zero)
   unsigned long long *C[kMaxBatch];
   long long pitchC[kMaxBatch];   // words
   int m;                         // rows of A / C
+  int l;                         // rows of B
+  int a3d;                       // m % 256 == 0: a tile's A slab is ONE 3D TMA box
   int nwordsC;                   // 64-bit words per C row that may be written
   int tiles_m;
   int tiles_n;
@@ -92,8 +96,8 @@ L2_FN void build_tables(uint32_t tbuf, uint32_t bstep, int tid) {
   constexpr int E  = 2048 / NT;
   constexpr int GB = E == 8 ? 3 : (E == 4 ? 2 : -1);
   static_assert(GB > 0, "unsupported thread count");
-  int const c = tid & 7, t = c & 3, h = c >> 2, g = tid >> 3;
-  uint32_t const src = bstep + t * (kBBoxBytes + 32) + h * 16;
+  int const c = tid & 7, g = tid >> 3;                      // c = 4*h + t
+  uint32_t const src = bstep + c * 16;
   U4 low[GB];
 #pragma unroll
   for (int b = 0; b < GB; ++b) low[b] = lds128(src + b * 128);
@@ -143,28 +147,33 @@ L2_FN void lookup_row(U4 &acc0, U4 &acc1, uint32_t a, uint32_t const (&base)[4],
   dep = (acc0.x ^ acc0.y ^ acc0.z) ^ (acc0.w ^ acc1.x ^ acc1.y) ^ (acc1.z ^ acc1.w);
 }
 
-// TMA for K-slab `kslab` of the current segment into ring slot `slot`: 16 boxes of A (256 rows x 16 B) and
-// 16 boxes of B (one per table: 8 rows x 128 B, see kBBoxBytes).  TMA instructions are issued one thread
-// at a time, so the 32 of a slab are spread over the warps (lanes 0-3 of warp w take operations 4w .. 4w+3):
-// no warp falls more than four issue slots behind the others at the next barrier.  complete_tx may overtake
-// thread 0's arrive.expect_tx — the phase cannot complete before that arrival, the tx-count is signed.
-template <int NT>
-L2_FN void issue_slab(Args const &p, uint32_t sbase, int tid, int prob, int tn, int row0, int kslab, uint32_t slot) {
+// A: TMA for K-slab `kslab` (128 columns) of the tile rows [row0, row0 + 4096) into ring slot `slot`, issued
+// by thread 0: one 3D box when the row count allows it (the 3D view groups rows by 256, so its last group
+// must be complete), else sixteen 2D boxes.  Rows / columns outside the matrix arrive as zeros.
+L2_FN void issue_a(Args const &p, uint32_t sbase, int tid, int prob, int row0, int kslab, uint32_t slot) {
+  if (tid != 0) return;
   uint32_t const bar = sbase + kOffBar + 8u * slot;
-  if (tid == 0) mbar_expect_tx(bar, kSlabTxBytes);
-  constexpr int kOpsPerWarp = 32 / (NT / 32);
-  int const lane = tid & 31;
-  if (lane < kOpsPerWarp) {
-    int const op = (tid >> 5) * kOpsPerWarp + lane;
-    if (op < kAParts)
-      tma_load_2d(sbase + kOffA + slot * kASlabBytes + op * (kABoxRows * 16), &p.mapA[prob], kslab * 4,
-                  row0 + op * kABoxRows, bar);
-    else {
-      int const box = op - kAParts;                // table box & 3 of step box >> 2
-      tma_load_2d(sbase + kOffB + slot * kBSlabBytes + box * kBBoxBytes, &p.mapB[prob], tn * 8 - 8 * (box & 3),
-                  kslab * kSlabBits + box * 8, bar);
-    }
+  uint32_t const dst = sbase + kOffA + slot * kASlabBytes;
+  mbar_expect_tx(bar, kSlabTxBytes);
+  if (p.a3d) {
+    tma_load_3d(dst, &p.mapA[prob], kslab * 4, 0, row0 / kABoxRows, bar);
+  } else {
+    for (int part = 0; part < kAParts; ++part)
+      tma_load_2d(dst + part * (kABoxRows * 16), &p.mapA[prob], kslab * 4, row0 + part * kABoxRows, bar);
   }
+}
+
+// B: this thread's 16-byte piece of K-slab `kslab`, tile column tn, into ring slot `slot` (see kBStepBytes).
+// Rows >= l and pieces past the row pitch are zero-filled (cp.async with a source size of 0).
+template <int NT>
+L2_FN void prefetch_b(Args const &p, uint32_t sbase, int tid, int prob, int tn, int kslab, uint32_t slot) {
+  static_assert(NT == 256, "one 16-byte piece of the 4 KB B slab per thread");
+  int const h = tid & 1, t = (tid >> 1) & 3, b = (tid >> 3) & 7, st = tid >> 6;
+  int const row = kslab * kSlabBits + st * 32 + t * 8 + b;
+  long long const piece = (long long)tn * 2 + h;                 // 16-byte pieces along the row
+  bool const valid = row < p.l && piece * 2 < p.pitchB[prob];
+  unsigned long long const *src = p.B[prob] + (valid ? (long long)row * p.pitchB[prob] + piece * 2 : 0);
+  cp_async16(sbase + kOffB + slot * kBSlabBytes + st * kBStepBytes + b * kLineBytes + (h * 4 + t) * 16, src, valid ? 16u : 0u);
 }
 
 // The persistent stream-K CTA.  sbase = shared-memory address of the dynamic segment (1024-byte aligned),
@@ -206,21 +215,29 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
       nseg = p.slabs - s0;
       if (nseg > u_end - u) nseg = u_end - u;
       if (tid == 0) sts128(sSeg, U4{(uint32_t)prob, (uint32_t)tn, (uint32_t)(tm * kTM), (uint32_t)s0});
-      issue_slab<NT>(p, sbase, tid, prob, tn, tm * kTM, s0, ring & 1u);
-      if (nseg > 1) issue_slab<NT>(p, sbase, tid, prob, tn, tm * kTM, s0 + 1, (ring + 1u) & 1u);
+      issue_a(p, sbase, tid, prob, tm * kTM, s0, ring & 1u);
+      if (nseg > 1) issue_a(p, sbase, tid, prob, tm * kTM, s0 + 1, (ring + 1u) & 1u);
+      prefetch_b<NT>(p, sbase, tid, prob, tn, s0, ring & 1u);
+      cp_async_wait_all();
     }
 
     U4 acc[RT][2];
 #pragma unroll
     for (int j = 0; j < RT; ++j) acc[j][0] = acc[j][1] = U4{0u, 0u, 0u, 0u};
 
-    mbar_wait(sBar + 8u * (ring & 1u), (ring >> 1) & 1u);
+    cta_sync();                                     // every thread's piece of the first B slab has landed
     build_tables<NT>(sTab, sB + (ring & 1u) * kBSlabBytes, tid);
     cta_sync();
 
     for (int i = 0; i < nseg; ++i) {
       uint32_t const n = ring + (uint32_t)i, slot = n & 1u;
       uint32_t const bS = sB + slot * kBSlabBytes;
+      // B of the next slab: its slot was last read by the table builds of the previous slab's third step;
+      // the copy is awaited before the barrier that ends step 2 and consumed by the build of step 3
+      if (i + 1 < nseg) {
+        U4 const seg = lds128(sSeg);
+        prefetch_b<NT>(p, sbase, tid, (int)seg.x, (int)seg.y, (int)seg.w + i + 1, slot ^ 1u);
+      }
       // A bits of SP steps per load: one u32 per row and step, bytes rotated by the lane's table phase.
       // AWIDE = 0: an LDS.64 per row and half slab (4 wavefronts per 32 rows for 2 steps);
       // AWIDE = 1: an LDS.128 per row and slab (4 wavefronts for 4 steps, but 32 more live registers).
@@ -233,12 +250,12 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
           uint32_t const tnext = sTab + ((S & 1) ^ 1) * kStepBufBytes;
           // ---- tables of the next step into the other buffer ----
           if constexpr (S < kStepsPerSlab - 1) {
-            build_tables<NT>(tnext, bS + (S + 1) * 4 * kBBoxBytes, tid);
+            build_tables<NT>(tnext, bS + (S + 1) * kBStepBytes, tid);
           } else if (i + 1 < nseg) {
-            mbar_wait(sBar + 8u * (slot ^ 1u), ((n + 1u) >> 1) & 1u);
             build_tables<NT>(tnext, sB + (slot ^ 1u) * kBSlabBytes, tid);
           }
           // ---- A bits of the next SP steps (after the build: its registers are dead by now) ----
+          if constexpr (S == 0) mbar_wait(sBar + 8u * slot, (n >> 1) & 1u);      // this slab's A has landed
           if constexpr (S % SP == 0) {
 #pragma unroll
             for (int j = 0; j < RT; ++j) {
@@ -260,6 +277,7 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
 #pragma unroll
           for (int j = 0; j < RT; ++j)
             lookup_row<(S & 1) * kStepBufBytes>(acc[j][0], acc[j][1], aw[j][S % SP], base, dep, p.zero);
+          if constexpr (S == kStepsPerSlab - 2) cp_async_wait_all();
           cta_sync();
         };
         step(IntC<SP * P>{});
@@ -274,7 +292,7 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
       // ring slot `slot` is free again: refill it with slab i+2 of the segment
       if (i + 2 < nseg) {
         U4 const seg = lds128(sSeg);
-        issue_slab<NT>(p, sbase, tid, (int)seg.x, (int)seg.y, (int)seg.z, (int)seg.w + i + 2, slot);
+        issue_a(p, sbase, tid, (int)seg.x, (int)seg.z, (int)seg.w + i + 2, slot);
       }
     }
 

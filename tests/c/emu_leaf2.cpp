@@ -37,11 +37,11 @@ struct U4 {
 struct U2 {
   uint32_t x, y;
 };
-struct TMap {                 // what cuTensorMapEncodeTiled describes: a 2D u32 tensor and a box
+struct TMap {                 // what cuTensorMapEncodeTiled describes: a 2D / 3D u32 tensor and a box
   uint32_t const *base;
-  long dim0, dim1;            // u32 words per row, rows
-  long stride32;              // u32 words between rows
-  int box0, box1;
+  long dim0, dim1, dim2;      // u32 words per row, rows (per group), row groups
+  long stride1, stride2;      // u32 words between rows / between groups
+  int box0, box1, box2;
 };
 
 constexpr int kEmuThreads = 256;
@@ -125,25 +125,43 @@ L2_FN void mbar_wait(uint32_t bar, uint32_t parity) {
   EmuMbar &b = bar_at(bar);
   while ((b.phase.load() & 1u) == parity) std::this_thread::yield();
 }
-L2_FN void tma_load_2d(uint32_t dst, TMap const *map, int c0, int c1, uint32_t bar) {
+L2_FN void tma_load_3d(uint32_t dst, TMap const *map, int c0, int c1, int c2, uint32_t bar) {
   if (dst % 128) {
     fprintf(stderr, "emu: TMA destination %u not 128-byte aligned\n", dst);
     abort();
   }
-  uint32_t const bytes = (uint32_t)map->box0 * map->box1 * 4;
+  uint32_t const bytes = (uint32_t)map->box0 * map->box1 * map->box2 * 4;
   check_range(dst, 16);
   check_range(dst + bytes - 16, 16);
-  for (int r = 0; r < map->box1; ++r)
-    for (int c = 0; c < map->box0; ++c) {
-      long const x = (long)c0 + c, y = (long)c1 + r;
-      uint32_t v = 0;
-      if (x >= 0 && x < map->dim0 && y >= 0 && y < map->dim1) v = map->base[y * map->stride32 + x];
-      memcpy(g_smem + dst + ((size_t)r * map->box0 + c) * 4, &v, 4);
-    }
+  size_t o = 0;
+  for (int g = 0; g < map->box2; ++g)
+    for (int r = 0; r < map->box1; ++r)
+      for (int c = 0; c < map->box0; ++c, ++o) {
+        long const x = (long)c0 + c, y = (long)c1 + r, z = (long)c2 + g;
+        uint32_t v = 0;
+        if (x >= 0 && x < map->dim0 && y >= 0 && y < map->dim1 && z >= 0 && z < map->dim2)
+          v = map->base[z * map->stride2 + y * map->stride1 + x];
+        memcpy(g_smem + dst + o * 4, &v, 4);
+      }
   EmuMbar &b = bar_at(bar);
   b.tx.fetch_sub((long)bytes);
   bar_try_complete(b);
 }
+L2_FN void tma_load_2d(uint32_t dst, TMap const *map, int c0, int c1, uint32_t bar) {
+  if (map->box2 != 1) {
+    fprintf(stderr, "emu: 2D TMA with a 3D map\n");
+    abort();
+  }
+  tma_load_3d(dst, map, c0, c1, 0, bar);
+}
+L2_FN void cp_async16(uint32_t dst, void const *src, uint32_t src_bytes) {   // completes at once here
+  check_range(dst, 16);
+  if (src_bytes != 0 && src_bytes != 16) abort();
+  uint8_t tmp[16] = {0};
+  if (src_bytes) memcpy(tmp, src, 16);
+  memcpy(g_smem + dst, tmp, 16);
+}
+L2_FN void cp_async_wait_all() {}
 L2_FN void red_xor64(unsigned long long *p, uint32_t lo, uint32_t hi) {
   __atomic_fetch_xor(p, ((unsigned long long)hi << 32) | lo, __ATOMIC_RELAXED);
 }
@@ -181,9 +199,13 @@ void randomize(Mat &M) {
       M.w[(size_t)i * M.pitch + j] = v;
     }
 }
-TMap map_of(Mat const &M, int box0, int box1) {
-  return TMap{reinterpret_cast<uint32_t const *>(M.w.data()), (long)((M.ncols + 127) / 128) * 4, M.nrows, M.pitch * 2,
-              box0, box1};
+TMap map_of(Mat const &M, int box0, int box1) {      // 2D: words x rows
+  return TMap{reinterpret_cast<uint32_t const *>(M.w.data()), (long)((M.ncols + 127) / 128) * 4, M.nrows, 1,
+              M.pitch * 2, 0, box0, box1, 1};
+}
+TMap map_row_groups(Mat const &M, int box0, int group_rows, int box_groups) {   // 3D: words x 256 rows x groups
+  return TMap{reinterpret_cast<uint32_t const *>(M.w.data()), (long)((M.ncols + 127) / 128) * 4, group_rows,
+              M.nrows / group_rows, M.pitch * 2, M.pitch * 2 * group_rows, box0, group_rows, box_groups};
 }
 
 // C ^= A*B by definition, row-wise (reference semantics: m4ri/mzd.c:1141-1268 _mzd_mul_naive)
@@ -210,6 +232,8 @@ bool run_case(int count, int m, int l, int n, int nblocks) {
   Args p;
   memset(&p, 0, sizeof p);
   p.m = m;
+  p.l = l;
+  p.a3d = m % kABoxRows == 0 ? 1 : 0;
   p.nwordsC = (n + 63) / 64;
   p.tiles_m = (m + kTM - 1) / kTM;
   p.tiles_n = (n + kTileBits - 1) / kTileBits;
@@ -220,8 +244,9 @@ bool run_case(int count, int m, int l, int n, int nblocks) {
   for (int i = 0; i < count; ++i) {
     p.C[i] = reinterpret_cast<unsigned long long *>(C[i].w.data());
     p.pitchC[i] = C[i].pitch;
-    p.mapA[i] = map_of(A[i], 4, kABoxRows);
-    p.mapB[i] = map_of(B[i], 32, 8);
+    p.mapA[i] = p.a3d ? map_row_groups(A[i], 4, kABoxRows, kAParts) : map_of(A[i], 4, kABoxRows);
+    p.B[i] = reinterpret_cast<unsigned long long const *>(B[i].w.data());
+    p.pitchB[i] = B[i].pitch;
   }
   if (nblocks > p.total_units) nblocks = (int)p.total_units;
   g_bar_base = kEmuSbase + kOffBar;
@@ -272,8 +297,7 @@ bool check_bank_groups() {
   for (int b = 0; b < 8; ++b) {
     unsigned seen_ld = 0, seen_st = 0;
     for (int c = 0; c < 8; ++c) {
-      int const t = c & 3, h = c >> 2;
-      uint32_t const src = (uint32_t)(t * (kBBoxBytes + 32) + h * 16 + b * 128);
+      uint32_t const src = (uint32_t)(c * 16 + b * 128);
       seen_ld |= 1u << ((src / 16) & 7);
       seen_st |= 1u << (((uint32_t)c * 16 / 16) & 7);
     }
