@@ -223,42 +223,51 @@ def run_own_arm(args):
         raise SystemExit("n must be a multiple of 128 * gpus")
     cutoff = args.cutoff
     from m4ri_b200 import shard
-    r0, r1 = shard.row_blocks(n, world)[rank]
-    rows = r1 - r0                         # this rank's row-block of A and C
-    brow = shard.padded_slice_rows(n, world)   # this rank's row-slice of B (n % (64*world) == 0: no padding)
-    pitch = n // 64
+    # C is cut into pr row-blocks x pc column-blocks (pc = 2 from 4 ranks on, see m4ri_b200/shard.py):
+    # this rank owns C[rows gr, cols gc] = A[rows gr, :] * B[:, cols gc]
+    pr, pc = shard.grid_shape(world, args.grid)
+    gr, gc = shard.grid_coords(rank, world, args.grid)
+    r0, r1 = shard.row_blocks(n, pr)[gr]
+    c0, c1 = shard.col_blocks(n, pc)[gc]
+    rows, ncb = r1 - r0, c1 - c0           # this rank's block of C; A block is rows x n, B block n x ncb
+    brow = shard.padded_slice_rows(n, pr)  # this rank's row-slice of B[:, cols gc] (n % (64*world) == 0: no padding)
+    pitch, pitchb = n // 64, ncb // 64
+    group = None
+    if world > 1 and pc > 1:               # every rank creates every column group, in the same order
+        groups = [dist.new_group(shard.column_group(g, world, args.grid)) for g in range(pc)]
+        group = groups[gc]
 
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
     sh = ctypes.c_void_p(tstream.cuda_stream)
 
-    # ---- host inputs (pinned): A row-block, B row-slice, C row-block -------------------------
+    # ---- host inputs (pinned): A row-block, B piece, C block -------------------------------------
     pin = not args.pageable
     hA = torch.empty((rows, pitch), dtype=torch.int64, pin_memory=pin)
-    hB = torch.empty((brow, pitch), dtype=torch.int64, pin_memory=pin)
-    hC = torch.zeros((rows, pitch), dtype=torch.int64, pin_memory=pin)
-    fill_random_words(hA.numpy().view(np.uint64), 1000 + rank)
+    hB = torch.empty((brow, pitchb), dtype=torch.int64, pin_memory=pin)
+    hC = torch.zeros((rows, pitchb), dtype=torch.int64, pin_memory=pin)
+    fill_random_words(hA.numpy().view(np.uint64), 1000 + gr)          # ranks of one row-block share A's rows
     fill_random_words(hB.numpy().view(np.uint64), 2000 + rank)
     mA = make_header(MzdT, hA.data_ptr(), rows, n, pitch)
-    mB = make_header(MzdT, hB.data_ptr(), brow, n, pitch)
-    mC = make_header(MzdT, hC.data_ptr(), rows, n, pitch)
+    mB = make_header(MzdT, hB.data_ptr(), brow, ncb, pitchb)
+    mC = make_header(MzdT, hC.data_ptr(), rows, ncb, pitchb)
 
     # ---- device matrices (torch owns the memory; the library sees plain pointers) --------------
     tA = torch.zeros((rows, pitch), dtype=torch.int64, device="cuda")
-    tBs = torch.zeros((brow, pitch), dtype=torch.int64, device="cuda")
-    tB = tBs if world == 1 else torch.zeros((n, pitch), dtype=torch.int64, device="cuda")
-    tC = torch.zeros((rows, pitch), dtype=torch.int64, device="cuda")
+    tBs = torch.zeros((brow, pitchb), dtype=torch.int64, device="cuda")
+    tB = tBs if pr == 1 else torch.zeros((n, pitchb), dtype=torch.int64, device="cuda")
+    tC = torch.zeros((rows, pitchb), dtype=torch.int64, device="cuda")
     dA = lib.m4ri_b200_dmat_wrap(tA.data_ptr(), pitch, rows, n)
-    dBs = lib.m4ri_b200_dmat_wrap(tBs.data_ptr(), pitch, brow, n)
-    dB = lib.m4ri_b200_dmat_wrap(tB.data_ptr(), pitch, n, n)
-    dC = lib.m4ri_b200_dmat_wrap(tC.data_ptr(), pitch, rows, n)
+    dBs = lib.m4ri_b200_dmat_wrap(tBs.data_ptr(), pitchb, brow, ncb)
+    dB = lib.m4ri_b200_dmat_wrap(tB.data_ptr(), pitchb, n, ncb)
+    dC = lib.m4ri_b200_dmat_wrap(tC.data_ptr(), pitchb, rows, ncb)
     lib.m4ri_b200_upload(dA, ctypes.byref(mA), sh)
     lib.m4ri_b200_upload(dBs, ctypes.byref(mB), sh)
     torch.cuda.synchronize()
 
     def exchange():
-        if world > 1:  # the path's one exchange step: all-gather of B's row-slices over NVLink
-            dist.all_gather_into_tensor(tB.view(-1), tBs.view(-1))
+        if pr > 1:  # the path's one exchange step: all-gather of the row-slices of B[:, cols gc] over NVLink
+            dist.all_gather_into_tensor(tB.view(-1), tBs.view(-1), group=group)
 
     def step_resident():
         exchange()
@@ -326,20 +335,46 @@ def run_own_arm(args):
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     e2e_value = total_bitops / e2e_s
-    h2d = (rows + brow) * pitch * 8 * world
-    d2h = rows * pitch * 8 * world
+    h2d = (rows * pitch + brow * pitchb) * 8 * world
+    d2h = rows * pitchb * 8 * world
 
     if args.verify:   # small-n correctness of this rank's block against the oracle (never at full size)
         from tests import harness as H
         step_e2e()
-        full_b = torch.empty((n, pitch), dtype=torch.int64)
-        full_b.copy_(tB)
-        Ao, Bo = H.new(rows, n), H.new(n, n)
+        col_b = torch.empty((n, pitchb), dtype=torch.int64)
+        col_b.copy_(tB)
+        Ao, Bo = H.new(rows, n), H.new(n, ncb)
         H.storage(Ao)[:, :] = hA.numpy().view(np.uint64)
-        H.storage(Bo)[:, :] = full_b.numpy().view(np.uint64)
+        H.storage(Bo)[:, :] = col_b.numpy().view(np.uint64)
         want = H.oracle().orc_mul(None, Ao, Bo, 0)
         ok = bool(np.array_equal(H.storage(want), hC.numpy().view(np.uint64)))
-        print(f"[verify] rank {rank}: rows {r0}:{r1} {'OK' if ok else 'MISMATCH'}", file=sys.stderr, flush=True)
+        print(f"[verify] rank {rank}: rows {r0}:{r1} cols {c0}:{c1} {'OK' if ok else 'MISMATCH'}", file=sys.stderr, flush=True)
+        if not ok:
+            raise SystemExit(3)
+
+    if args.check:    # any size, on the device: the exchange delivered the pieces in order, and Freivalds on this
+        #               rank's block with 128 random vectors: C_blk * X == A_blk * (B_colblk * X)   (error 2^-128)
+        step_resident()
+        torch.cuda.synchronize()
+        ok = True
+        if pr > 1:
+            mine = tBs.sum().reshape(1)
+            sums = torch.empty(pr, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(sums, mine, group=group)
+            ok = bool(torch.equal(tB.view(pr, brow, pitchb).sum(dim=(1, 2)), sums))
+        tX = torch.randint(-2**62, 2**62, (ncb, 2), dtype=torch.int64, device="cuda")
+        tY = torch.zeros((n, 2), dtype=torch.int64, device="cuda")
+        tZ = torch.zeros((rows, 2), dtype=torch.int64, device="cuda")
+        tW = torch.zeros((rows, 2), dtype=torch.int64, device="cuda")
+        dX, dY = lib.m4ri_b200_dmat_wrap(tX.data_ptr(), 2, ncb, 128), lib.m4ri_b200_dmat_wrap(tY.data_ptr(), 2, n, 128)
+        dZ, dW = lib.m4ri_b200_dmat_wrap(tZ.data_ptr(), 2, rows, 128), lib.m4ri_b200_dmat_wrap(tW.data_ptr(), 2, rows, 128)
+        torch.cuda.synchronize()
+        lib.m4ri_b200_dmul_m4rm(dY, dB, dX, 1, sh)
+        lib.m4ri_b200_dmul_m4rm(dZ, dA, dY, 1, sh)
+        lib.m4ri_b200_dmul_m4rm(dW, dC, dX, 1, sh)
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(tZ, tW)) and bool(tZ.any())
+        print(f"[check] rank {rank}: rows {r0}:{r1} cols {c0}:{c1} {'OK' if ok else 'MISMATCH'}", file=sys.stderr, flush=True)
         if not ok:
             raise SystemExit(3)
 
@@ -368,7 +403,7 @@ def run_own_arm(args):
     leaf_dims = None
     try:
         lv = int(path.split(":")[1]) if ":" in path else 0
-        leaf_dims = (rows >> lv, n >> lv, n >> lv)
+        leaf_dims = (rows >> lv, n >> lv, ncb >> lv)
     except ValueError:
         lv = 0
     # compulsory HBM bytes of one leaf launch: read A and B once, RMW C once
@@ -415,7 +450,7 @@ def run_own_arm(args):
         a1.record()
         torch.cuda.synchronize()
         add_ms = a0.elapsed_time(a1) / 10
-        add_bytes = 3.0 * rows * pitch * 8           # 2 reads + 1 write, every byte once
+        add_bytes = 3.0 * rows * pitch * 8           # 2 reads + 1 write, every byte once (world == 1: all n x n)
         add_gbs = add_bytes / (add_ms * 1e-3) / 1e9
         add_roofline = {"kernel": "ew_kernel<0> (_mzd_add)", "bound": "hbm", "unit": "GB/s", "achieved": add_gbs,
                         "peak": hbm_peak, "frac": add_gbs / hbm_peak, "ms": add_ms,
@@ -433,7 +468,11 @@ def run_own_arm(args):
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": f"mzd_mul {n}x{n}x{n} random GF(2), Strassen-Winograd + M4RM leaf (BASELINE config "
                                f"{'3' if world == 1 else '4'})", "n": n, "cutoff": cutoff or lib.m4ri_b200_get_default_cutoff(),
-                   "path": path, "parallelism": f"row-block x{world}" + (", NCCL all-gather of B per step" if world > 1 else ""),
+                   "path": path,
+                   "parallelism": (f"row-block x{world}" if pc == 1 else f"C blocks {pr} x {pc} (row-blocks x column-blocks)") +
+                                  ("" if world == 1 else ", NCCL all-gather of B per step" if pc == 1 else
+                                   f", NCCL all-gather of B's column block inside each column group ({pr} ranks) per step"),
+                   "local_product": [rows, n, ncb],
                    "l2": "inputs (3 x %d MiB) exceed the 126 MB L2; no flush needed" % (n * n // 8 >> 20)},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "host_memory": "pageable" if args.pageable else "pinned",
@@ -461,6 +500,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--pageable", action="store_true", help="e2e with pageable (malloc) host matrices instead of pinned")
+    ap.add_argument("--grid", default="auto", choices=["auto", "rows"],
+                    help="C partition over ranks: 'rows' = row-blocks only; 'auto' = two column blocks from 4 ranks on")
+    ap.add_argument("--check", action="store_true", help="device-side check at any size: exchange order + Freivalds on this rank's block")
     ap.add_argument("--verify", action="store_true", help="check this rank's C block against the oracle (small --n only)")
     args = ap.parse_args()
     if args.impl == "reference":

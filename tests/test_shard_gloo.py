@@ -89,3 +89,85 @@ def test_sharded_product_over_gloo(world, shape):
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+# ---- 2D grid (world >= 4): row-blocks x two column blocks, all-gather inside each column group -----------
+
+def test_grid_helpers():
+    assert [shard.grid_shape(w) for w in (1, 2, 3, 4, 6, 8)] == [(1, 1), (2, 1), (3, 1), (2, 2), (3, 2), (4, 2)]
+    assert shard.grid_shape(8, "rows") == (8, 1)
+    for world in (4, 6, 8):
+        pr, pc = shard.grid_shape(world)
+        seen = set()
+        for rank in range(world):
+            gr, gc = shard.grid_coords(rank, world)
+            assert 0 <= gr < pr and 0 <= gc < pc and (gr, gc) not in seen
+            seen.add((gr, gc))
+            grp = shard.column_group(rank, world)
+            assert rank in grp and len(grp) == pr and grp == sorted(grp)
+            assert all(shard.grid_coords(r, world)[1] == gc for r in grp)
+            assert [shard.grid_coords(r, world)[0] for r in grp] == list(range(pr))   # gather order = row-slice order
+    blocks = shard.col_blocks(65536, 2)
+    assert blocks == [(0, 32768), (32768, 65536)]
+    assert all(c0 % 128 == 0 for c0, _ in shard.col_blocks(1000, 2)) and shard.col_blocks(1000, 2)[-1][1] == 1000
+
+
+def _worker2d(rank, world, port, m, l, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pr, pc = shard.grid_shape(world)
+    gr, gc = shard.grid_coords(rank, world)
+    groups = [dist.new_group(shard.column_group(g, world)) for g in range(pc)]
+    rng = np.random.default_rng(43)                       # every rank derives the same full inputs
+    assert n % 64 == 0 and l % 64 == 0                    # whole words: column blocks are cut on word boundaries here
+    wl, wn = l // 64, n // 64
+    A = rng.integers(0, 2**64, size=(m, wl), dtype=np.uint64)
+    B = rng.integers(0, 2**64, size=(l, wn), dtype=np.uint64)
+    r0, r1 = shard.row_blocks(m, pr)[gr]
+    c0, c1 = shard.col_blocks(n, pc)[gc]
+    w0, w1 = c0 // 64, (c1 + 63) // 64
+    per = shard.padded_slice_rows(l, pr)
+    s0, s1 = min(l, gr * per), min(l, (gr + 1) * per)
+    b_piece = np.zeros((per, w1 - w0), dtype=np.uint64)
+    b_piece[: s1 - s0] = B[s0:s1, w0:w1]
+
+    def group_all_gather(piece, ranks):
+        assert ranks == shard.column_group(rank, world)
+        out = torch.empty((len(ranks) * per, piece.shape[1]), dtype=torch.int64)
+        dist.all_gather_into_tensor(out.view(-1), torch.from_numpy(piece.view(np.int64)).reshape(-1), group=groups[gc])
+        return out.numpy().view(np.uint64)
+
+    def local_mul(a_blk, b_col):
+        if a_blk.shape[0] == 0 or c1 == c0:
+            return np.zeros((a_blk.shape[0], w1 - w0), dtype=np.uint64)
+        Am, Bm = _matrix_from(a_blk, l), _matrix_from(b_col[:l], c1 - c0)
+        Cm = H.oracle().orc_mul(None, Am, Bm, 0)
+        out = H.storage(Cm)[:, : w1 - w0].copy()
+        H.free(Am, Bm, Cm)
+        return out
+
+    c_blk = shard.sharded_product_2d(rank, world, A[r0:r1], b_piece, group_all_gather, local_mul)
+    gathered = [None] * world
+    dist.gather_object((r0, r1, w0, w1, c_blk), gathered if rank == 0 else None, dst=0)
+    if rank == 0:
+        C = np.zeros((m, wn), dtype=np.uint64)
+        for g0, g1, v0, v1, blk in gathered:
+            C[g0:g1, v0:v1] = blk
+        Am, Bm = _matrix_from(A, l), _matrix_from(B, n)
+        want = H.oracle().orc_mul(None, Am, Bm, 0)
+        q.put(bool(np.array_equal(C, H.storage(want)[:, :wn])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(4, (300, 256, 512)), (4, (130, 1024, 256)), (6, (200, 320, 384))])
+def test_grid_product_over_gloo(world, shape):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + world * 11 + shape[0]) % 2000
+    procs = [ctx.Process(target=_worker2d, args=(r, world, port, *shape, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
