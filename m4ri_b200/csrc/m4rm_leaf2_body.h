@@ -6,7 +6,7 @@
 //     lookups  TM*W/8   +   table stores 256*W/8   +   table-build reads   +   A words
 // bytes of shared-memory traffic for TM x 8W bits of C (W = tile row bytes, TM*W = 128 KB of registers).
 // The first leaf (TM = 1024, W = 128) spends 20 % of its wavefronts on building tables; TM = 4096, W = 32
-// cuts the build to 1/4 per C bit: 148 instead of 168 wavefronts per A column and 128 KB of C.
+// cuts the build to 1/4 per C bit: 152 instead of 168 wavefronts per A column and 128 KB of C.
 //
 // What makes W = 32 work on 32 banks: FOUR tables (32 columns of A = one u32 per row) are interleaved
 // in one 128-byte line per index value — piece (h, t) = 16-byte half h of the entry of table t sits at byte
@@ -14,11 +14,17 @@
 // the other half of the same entry in the next one: eight lanes, eight different 16-byte bank groups, for
 // ANY eight index values.  Every LDS.128 wavefront therefore carries 128 useful bytes and serves 8 C rows.
 //
+// Operands: A by TMA (one 3D box per 128-column slab and 4096-row tile), B by cp.async (4 KB per slab: one
+// 16-byte piece per thread, placed directly in the layout the table build reads), both zero-filled outside
+// the matrices, which is what makes ragged m / l / n edges free.  Stream-K over (problem, tile, slab) units
+// with red.global.xor merges, as in the first leaf.
+//
 // This header is compiled twice: by nvcc inside m4rm_leaf2.cu, and by g++ inside tests/c/emu_leaf2.cpp,
-// where a CTA is 256 host threads, shared memory an array, TMA a host copy and the mbarriers/atomics are
-// emulated — so the index arithmetic of this file is tested on the CPU (tests/test_leaf2_emu.py) without
-// being restated.  The includer provides: L2_FN, U4, U2, TMap, lds128, lds64, sts128, prmt, mbar_wait,
-// mbar_expect_tx, tma_load_2d, tma_load_3d, cp_async16, cp_async_wait_all, red_xor64, cta_sync, gate(a, b, c) = a | (b & c); lds128 also as lds128<IMM>(addr) = [addr + IMM].
+// where a CTA is 256 host threads, shared memory an array, TMA / cp.async host copies and the mbarriers and
+// atomics are emulated — so the index arithmetic of this file is tested on the CPU (tests/test_leaf2_emu.py)
+// without being restated.  The includer provides: L2_FN, U4, U2, TMap, lds128, lds64, sts128, prmt,
+// mbar_wait, mbar_expect_tx, tma_load_2d, tma_load_3d, cp_async16, cp_async_wait_all, red_xor64, cta_sync,
+// gate(a, b, c) = a | (b & c); lds128 also as lds128<IMM>(addr) = [addr + IMM].
 #pragma once
 #include <stdint.h>
 
