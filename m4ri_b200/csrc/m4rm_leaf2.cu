@@ -94,7 +94,7 @@ L2_FN uint32_t gate(uint32_t a, uint32_t b, uint32_t c) {   // a | (b & c) as ON
 
 namespace leaf2 {
 
-template <int NT, int AWIDE>
+template <int NT, int AWIDE, int SPLIT>
 __global__ void __launch_bounds__(NT, 1) m4rm_leaf2_kernel(const __grid_constant__ Args p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint32_t const sbase = smem_u32(smem);
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NT, 1) m4rm_leaf2_kernel(const __grid_constant
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  cta_body<NT, AWIDE>(p, sbase, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+  cta_body<NT, AWIDE, SPLIT>(p, sbase, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 }  // namespace leaf2
@@ -114,6 +114,7 @@ namespace m4b {
 
 namespace {
 constexpr int kThreads = 256;
+constexpr int kDefaultSplit = 0;   // table build by all warps (1: by alternating halves of the CTA)
 }
 
 // The tall tile only pays when its 4096 rows are (nearly) all real rows: rows past m are zero-filled by the
@@ -127,13 +128,17 @@ bool leaf2_suits(int m, int l, int n) {
 // C ^= A*B for `count` (<= 7) products of identical shape in one persistent launch.
 void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *B, cudaStream_t stream) {
   using namespace leaf2;
-  // experiment knob: M4RI_B200_LEAF2_AWIDE=1 loads the A bits of a whole slab per row with one LDS.128
-  static int const awide = [] {
-    char const *env = getenv("M4RI_B200_LEAF2_AWIDE");
-    return env && env[0] == '1' ? 1 : 0;
+  // experiment knobs: M4RI_B200_LEAF2_AWIDE=1 loads the A bits of a whole slab per row with one LDS.128;
+  // M4RI_B200_LEAF2_SPLIT=0|1 lets all / half of the warps build the tables of a step
+  static int const variant = [] {
+    char const *a = getenv("M4RI_B200_LEAF2_AWIDE"), *s = getenv("M4RI_B200_LEAF2_SPLIT");
+    if (a && a[0] == '1') return 1;
+    if (s && (s[0] == '0' || s[0] == '1')) return s[0] == '1' ? 2 : 0;
+    return kDefaultSplit ? 2 : 0;
   }();
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
-  auto kern = awide ? m4rm_leaf2_kernel<kThreads, 1> : m4rm_leaf2_kernel<kThreads, 0>;
+  auto kern = variant == 1 ? m4rm_leaf2_kernel<kThreads, 1, 0>
+            : variant == 2 ? m4rm_leaf2_kernel<kThreads, 0, 1> : m4rm_leaf2_kernel<kThreads, 0, 0>;
   int dev = 0;
   M4B_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {

@@ -97,12 +97,17 @@ L2_FN void xor4(U4 &d, U4 const &a, U4 const &b) {   // one LOP3 per word
 // consecutive index values; base = XOR of the B rows selected by the high index bits, then a reflected
 // Gray walk over the low ones (one XOR + one STS.128 per entry, no table read-back).  A quarter-warp
 // stores one complete 128-byte line per instruction and loads eight different bank groups.
-template <int NT>
-L2_FN void build_tables(uint32_t tbuf, uint32_t bstep, int tid) {
-  constexpr int E  = 2048 / NT;
-  constexpr int GB = E == 8 ? 3 : (E == 4 ? 2 : -1);
-  static_assert(GB > 0, "unsupported thread count");
-  int const c = tid & 7, g = tid >> 3;                      // c = 4*h + t
+// NB = number of building threads: NT (every thread builds 8 entries) or NT/2 (the warps of one half of
+// the CTA — `half`, alternating from step to step — build 16 entries each: every thread loads all 8 B rows
+// of its piece column either way, so half the builders means half the B-row wavefronts).
+template <int NT, int NB>
+L2_FN void build_tables(uint32_t tbuf, uint32_t bstep, int tid, int half) {
+  constexpr int E  = 2048 / NB;
+  constexpr int GB = E == 16 ? 4 : (E == 8 ? 3 : -1);
+  static_assert(GB > 0 && (NB == NT || 2 * NB == NT), "unsupported builder count");
+  if (NB != NT && (tid / NB) != half) return;       // warp-uniform
+  int const bt = tid % NB;
+  int const c = bt & 7, g = bt >> 3;                // c = 4*h + t
   uint32_t const src = bstep + c * 16;
   U4 low[GB];
 #pragma unroll
@@ -121,15 +126,11 @@ L2_FN void build_tables(uint32_t tbuf, uint32_t bstep, int tid) {
   sts128(dst, e);
 #pragma unroll
   for (int i = 1; i < E; ++i) {
-    xor4(e, low[(i & 1) ? 0 : ((i & 2) ? 1 : 2)]);
+    xor4(e, low[(i & 1) ? 0 : ((i & 2) ? 1 : ((i & 4) ? 2 : 3))]);
     sts128(dst + (i ^ (i >> 1)) * kLineBytes, e);
   }
 }
 
-// Lookups of one step for one C row (replaces mzd_read_bits + _mzd_combine_8): a = the row's 32 A bits with
-// its bytes already rotated by the lane's table phase, so byte jj indexes table (i8 + jj) & 3 — the table
-// whose piece this lane reads in its jj-th load (base[jj] = lane part of the address, IMM = table buffer).
-// acc0 is the lane's "own" half (hl), acc1 the other one.
 // `dep` chains the rows of a thread: the A word of a row is OR-ed with (dep & zero) — still the A word, but
 // now data dependent on the last table line of the previous row — so a warp never has more than one row's
 // eight LDS.128 (32 registers) in flight.  Without the chain ptxas schedules for single-warp latency, keeps
@@ -189,9 +190,10 @@ L2_FN void prefetch_b(Args const &p, uint32_t sbase, int tid, int prob, int tn, 
 // round trip here (the 224 KB of shared memory leave almost no L1), so the per-segment scalars live in
 // shared memory (kOffSeg) and the ring state is ONE counter: K-slab number n of this CTA uses ring slot
 // n & 1 and mbarrier phase parity (n >> 1) & 1.
-template <int NT, int AWIDE>
+template <int NT, int AWIDE, int SPLIT>
 L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks) {
   constexpr int RT = kTM / NT;                      // rows per thread, each as two 16-byte pieces
+  constexpr int NB = SPLIT ? NT / 2 : NT;           // table-building threads per step
   uint32_t const sTab = sbase + kOffTables;
   uint32_t const sA   = sbase + kOffA;
   uint32_t const sB   = sbase + kOffB;
@@ -232,7 +234,7 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
     for (int j = 0; j < RT; ++j) acc[j][0] = acc[j][1] = U4{0u, 0u, 0u, 0u};
 
     cta_sync();                                     // every thread's piece of the first B slab has landed
-    build_tables<NT>(sTab, sB + (ring & 1u) * kBSlabBytes, tid);
+    build_tables<NT, NB>(sTab, sB + (ring & 1u) * kBSlabBytes, tid, 1);
     cta_sync();
 
     for (int i = 0; i < nseg; ++i) {
@@ -256,9 +258,9 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
           uint32_t const tnext = sTab + ((S & 1) ^ 1) * kStepBufBytes;
           // ---- tables of the next step into the other buffer ----
           if constexpr (S < kStepsPerSlab - 1) {
-            build_tables<NT>(tnext, bS + (S + 1) * kBStepBytes, tid);
+            build_tables<NT, NB>(tnext, bS + (S + 1) * kBStepBytes, tid, S & 1);
           } else if (i + 1 < nseg) {
-            build_tables<NT>(tnext, sB + (slot ^ 1u) * kBSlabBytes, tid);
+            build_tables<NT, NB>(tnext, sB + (slot ^ 1u) * kBSlabBytes, tid, S & 1);
           }
           // ---- A bits of the next SP steps (after the build: its registers are dead by now) ----
           if constexpr (S == 0) mbar_wait(sBar + 8u * slot, (n >> 1) & 1u);      // this slab's A has landed

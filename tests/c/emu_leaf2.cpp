@@ -25,6 +25,9 @@
 #include <vector>
 
 #define L2_FN inline
+#ifndef EMU_SPLIT
+#define EMU_SPLIT 0   // 1: half of the warps build the tables of a step
+#endif
 #ifndef EMU_AWIDE
 #define EMU_AWIDE 0   // which A-load variant of the kernel body to emulate
 #endif
@@ -264,7 +267,7 @@ bool run_case(int count, int m, int l, int n, int nblocks) {
           }
         }
         cta_sync();
-        cta_body<kEmuThreads, EMU_AWIDE>(p, kEmuSbase, tid, bid, nblocks);
+        cta_body<kEmuThreads, EMU_AWIDE, EMU_SPLIT>(p, kEmuSbase, tid, bid, nblocks);
         cta_sync();
       }
     });
