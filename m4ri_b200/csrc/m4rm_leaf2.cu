@@ -114,7 +114,7 @@ namespace m4b {
 
 namespace {
 constexpr int kThreads = 256;
-constexpr int kDefaultSplit = 0;   // table build by all warps (1: by alternating halves of the CTA)
+constexpr int kDefaultSplit = 1;   // tables of a step built by alternating halves of the CTA (+1.2 % measured); 0: by all warps
 }
 
 // The tall tile only pays when its 4096 rows are (nearly) all real rows: rows past m are zero-filled by the
