@@ -511,3 +511,42 @@ orc_mzd *orc_transpose(orc_mzd *D, orc_mzd const *A) {
   }
   return D;
 }
+
+/* ---- echelon forms (m4ri/mzd.c:208-233 mzd_gauss_delayed / mzd_echelonize_naive) -------------------------
+ * Column by column: the first row at or below `startrow` with a 1 in the column is swapped up and added to
+ * every other row that has a 1 there (full != 0: rows above as well -> reduced row echelon form, which is
+ * unique, so every correct algorithm — the reference's M4RI and PLUQ variants, tests/test_elimination.c —
+ * yields the same bits; full == 0: only the rows below).  Returns the rank. */
+orc_rci orc_echelonize(orc_mzd *M, int full) {
+  orc_rci startrow = 0, pivots = 0;
+  for (orc_rci i = 0; i < M->ncols; ++i) {
+    for (orc_rci j = startrow; j < M->nrows; ++j) {
+      if ((rowp(M, j)[i / RADIX] >> (i % RADIX)) & 1) {
+        if (j != startrow) {                       /* mzd_row_swap: valid words only */
+          orc_word *a = rowp(M, startrow), *b = rowp(M, j);
+          for (orc_wi w = 0; w < M->width; ++w) {
+            orc_word const mask = (w == M->width - 1) ? M->high_bitmask : ~(orc_word)0;
+            orc_word const t = (a[w] ^ b[w]) & mask;
+            a[w] ^= t;
+            b[w] ^= t;
+          }
+        }
+        ++pivots;
+        orc_word const *src = rowp(M, startrow);
+        for (orc_rci ii = full ? 0 : startrow + 1; ii < M->nrows; ++ii) {
+          if (ii == startrow) continue;
+          orc_word *dst = rowp(M, ii);
+          if ((dst[i / RADIX] >> (i % RADIX)) & 1) {   /* mzd_row_add_offset: from the word of column i on */
+            for (orc_wi w = i / RADIX; w < M->width; ++w) {
+              orc_word const mask = (w == M->width - 1) ? M->high_bitmask : ~(orc_word)0;
+              dst[w] ^= src[w] & mask;
+            }
+          }
+        }
+        ++startrow;
+        break;
+      }
+    }
+  }
+  return pivots;
+}

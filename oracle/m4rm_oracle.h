@@ -67,6 +67,9 @@ void     orc_trsm_upper_right(orc_mzd const *U, orc_mzd *B);
 /* DST = A^T (m4ri/mzd.c:1118-1139) */
 orc_mzd *orc_transpose(orc_mzd *DST, orc_mzd const *A);
 
+/* m4ri/mzd.c:208-233: (reduced) row echelon form in place, returns the rank */
+orc_rci  orc_echelonize(orc_mzd *M, int full);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ def oracle():
         lib.orc_trsm_lower_right.argtypes = [MzdP, MzdP]
         lib.orc_trsm_upper_right.argtypes = [MzdP, MzdP]
         lib.orc_transpose.argtypes, lib.orc_transpose.restype = [MzdP, MzdP], MzdP
+        lib.orc_echelonize.argtypes, lib.orc_echelonize.restype = [MzdP, c_int], c_int
         _oracle = lib
     return _oracle
 
@@ -82,6 +83,9 @@ def _declare_ref(lib):
     lib.mzd_make_table.argtypes = [MzdP, c_int, c_int, c_int, MzdP, POINTER(c_int)]
     lib.m4ri_random_word.restype = c_uint64
     lib.mzd_transpose.argtypes, lib.mzd_transpose.restype = [MzdP, MzdP], MzdP
+    lib.mzd_echelonize_m4ri.argtypes, lib.mzd_echelonize_m4ri.restype = [MzdP, c_int, c_int], c_int
+    lib.mzd_echelonize_naive.argtypes, lib.mzd_echelonize_naive.restype = [MzdP, c_int], c_int
+    lib.mzd_echelonize_pluq.argtypes, lib.mzd_echelonize_pluq.restype = [MzdP, c_int], c_int
     for name in ("mzd_trsm_lower_left", "mzd_trsm_upper_left", "mzd_trsm_lower_right", "mzd_trsm_upper_right"):
         getattr(lib, name).argtypes = [MzdP, MzdP, c_int]
         getattr(lib, name).restype = None
