@@ -152,6 +152,13 @@ mzd_t *m4ri_b200_transpose(mzd_t *DST, mzd_t const *A);
 /* C = A ^ B on device matrices (the device form of _mzd_add, m4ri/mzd.c:1471-1583). */
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream);
 
+/* Reduced row echelon form in place, returns the rank: the result of mzd_echelonize_m4ri(A, 1, k)
+ * (m4ri/brilliantrussian.h:79 via echelonform.h, m4ri/brilliantrussian.c:603-967).  The reduced form is unique,
+ * hence bit-identical to every reference variant; `full` is accepted for signature compatibility, the reduced form
+ * is returned either way.  The device form synchronises the stream (it returns the rank). */
+int   m4ri_b200_dechelonize(m4ri_b200_dmat *A, int full, void *stream);
+rci_t m4ri_b200_echelonize(mzd_t *A, int full);
+
 #ifdef __cplusplus
 }
 #endif

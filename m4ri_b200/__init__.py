@@ -99,6 +99,8 @@ def _declare(lib):
     lib.m4ri_b200_dtranspose.argtypes = [DMatP, DMatP, c_void_p]
     lib.m4ri_b200_transpose.argtypes, lib.m4ri_b200_transpose.restype = [MzdP, MzdP], MzdP
     lib.m4ri_b200_dadd.argtypes = [DMatP, DMatP, DMatP, c_void_p]
+    lib.m4ri_b200_dechelonize.argtypes, lib.m4ri_b200_dechelonize.restype = [DMatP, c_int, c_void_p], c_int
+    lib.m4ri_b200_echelonize.argtypes, lib.m4ri_b200_echelonize.restype = [MzdP, c_int], c_int
     return lib
 
 

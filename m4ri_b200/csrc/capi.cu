@@ -650,6 +650,35 @@ mzd_t *m4ri_b200_transpose(mzd_t *DST, mzd_t const *A) {
   return DST;
 }
 
+// Reduced row echelon form in place (the result of the reference's mzd_echelonize_m4ri(A, 1, k),
+// m4ri/brilliantrussian.c:603-967 — unique, so bit-identical); returns the rank.  full == 0 asks the reference for
+// *an* upper-triangular echelon form, which depends on its k; this library always returns the reduced one.
+int m4ri_b200_dechelonize(m4ri_b200_dmat *A, int full, void *stream) {
+  (void)full;
+  Ctx &c = ctx();
+  snprintf(c.last_path, sizeof c.last_path, "echelon");
+  c.ws.reserve(echelon_workspace_bytes(A->nrows, A->ncols));
+  return echelonize_device(as_view(A), c.ws, stream ? static_cast<cudaStream_t>(stream) : c.stream);
+}
+
+rci_t m4ri_b200_echelonize(mzd_t *A, int full) {
+  (void)full;
+  if (A->nrows == 0 || A->ncols == 0) return 0;
+  Ctx &c = ctx();
+  ++g_products;
+  snprintf(c.last_path, sizeof c.last_path, "echelon");
+  c.ws.reserve(Workspace::bytes_for(A->nrows, A->ncols) + echelon_workspace_bytes(A->nrows, A->ncols));
+  cudaStream_t s = c.stream;
+  DView dA = c.ws.alloc(A->nrows, A->ncols);
+  zero_async(dA, s);
+  upload(dA, A, s, &c.stager);
+  int const rank = echelonize_device(dA, c.ws, s);
+  download(A, dA, s, c.host_tmp, &c.stager);
+  M4B_CUDA(cudaStreamSynchronize(s));
+  c.ws.release(0);
+  return rank;
+}
+
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {
   if (A->nrows != B->nrows || A->ncols != B->ncols || C->nrows != A->nrows || C->ncols != A->ncols)
     die("m4ri_b200_dadd: dimension mismatch\n");

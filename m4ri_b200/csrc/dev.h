@@ -102,4 +102,8 @@ void   trsm_left(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaSt
 void   trsm_right(DView T, DView B, bool upper, int cutoff, Workspace &ws, cudaStream_t s);   // X T = B
 size_t trsm_workspace_bytes(int t, int m, int n, int cutoff);
 
+// ---- reduced row echelon form (echelon.cu) ----------------------------------------------------
+int    echelonize_device(DView A, Workspace &ws, cudaStream_t s);     // in place, returns the rank, synchronises s
+size_t echelon_workspace_bytes(int m, int n);
+
 }  // namespace m4b
