@@ -553,7 +553,10 @@ m4ri_b200_dmat *m4ri_b200_dmat_alloc(rci_t nrows, rci_t ncols) {
   size_t const bytes = (size_t)nrows * (size_t)M->pitch * 8;
   if (bytes) {
     M4B_CUDA(cudaMalloc(&M->data, bytes));
-    M4B_CUDA(cudaMemset(M->data, 0, bytes));
+    // on the library stream, and complete before returning: a memset on the legacy default stream is not ordered
+    // against the (non-blocking) library stream, so it could still be running when the first upload lands
+    M4B_CUDA(cudaMemsetAsync(M->data, 0, bytes, g.stream));
+    M4B_CUDA(cudaStreamSynchronize(g.stream));
   }
   return M;
 }

@@ -162,9 +162,26 @@ bool run_case(int m, int n, int rank_bound, int chunk_rows) {
 
 }  // namespace
 
+// matrix from a file of m * ceil(n/64) little-endian words (row major), e.g. written by a Python test
+bool run_file(char const *path, int m, int n, int chunk_rows) {
+  Mat A(m, n);
+  FILE *f = fopen(path, "rb");
+  if (!f) return false;
+  for (int i = 0; i < m; ++i)
+    if (fread(A.row(i), 8, (size_t)(n + 63) / 64, f) != (size_t)(n + 63) / 64) return false;
+  fclose(f);
+  Mat W = A;
+  int const want = rref_definition(W), got = device_rref_emulated(A, chunk_rows);
+  bool const ok = want == got && A.w == W.w;
+  printf("%s file %d x %d rank %d (emulated %d)\n", ok ? "ok  " : "FAIL", m, n, want, got);
+  return ok;
+}
+
 int main(int argc, char **argv) {
   bool ok = true;
-  if (argc == 5) {
+  if (argc == 6 && !strcmp(argv[1], "file")) {
+    ok = run_file(argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
+  } else if (argc == 5) {
     ok = run_case(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
   } else {
     struct Case {
