@@ -158,6 +158,9 @@ void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat c
  * is returned either way.  The device form synchronises the stream (it returns the rank). */
 int   m4ri_b200_dechelonize(m4ri_b200_dmat *A, int full, void *stream);
 rci_t m4ri_b200_echelonize(mzd_t *A, int full);
+/* B = A^-1 as mzd_inv_m4ri computes it (m4ri/brilliantrussian.h, m4ri/brilliantrussian.c:971-997): the right block of the
+ * reduced row echelon form of [A | I]; no invertibility test, B may be NULL (allocated). */
+mzd_t *m4ri_b200_inv_m4ri(mzd_t *B, mzd_t const *A);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ def _declare(lib):
     lib.m4ri_b200_dadd.argtypes = [DMatP, DMatP, DMatP, c_void_p]
     lib.m4ri_b200_dechelonize.argtypes, lib.m4ri_b200_dechelonize.restype = [DMatP, c_int, c_void_p], c_int
     lib.m4ri_b200_echelonize.argtypes, lib.m4ri_b200_echelonize.restype = [MzdP, c_int], c_int
+    lib.m4ri_b200_inv_m4ri.argtypes, lib.m4ri_b200_inv_m4ri.restype = [MzdP, MzdP], MzdP
     return lib
 
 

@@ -682,6 +682,35 @@ rci_t m4ri_b200_echelonize(mzd_t *A, int full) {
   return rank;
 }
 
+// B = A^-1 the way the reference computes it (mzd_inv_m4ri, m4ri/brilliantrussian.c:971-997): the right block of the
+// reduced row echelon form of [A | 0 | I] (the identity starts at the next 128-column boundary).  Like the reference
+// it does not test invertibility: for a singular A the result is still that (unique) block.  B may be NULL.
+mzd_t *m4ri_b200_inv_m4ri(mzd_t *B, mzd_t const *A) {
+  if (A->nrows != A->ncols) die("mzd_inv_m4ri: the matrix must be square.\n");
+  rci_t const n = A->nrows;
+  if (B == NULL) B = alloc_result(n, n);
+  else if (B->nrows != n || B->ncols != n) die("mzd_inv_m4ri: B has wrong dimensions.\n");
+  if (n == 0) return B;
+  int const np = round_up(n, 128);
+  Ctx &c = ctx();
+  ++g_products;
+  snprintf(c.last_path, sizeof c.last_path, "inverse");
+  c.ws.reserve(Workspace::bytes_for(n, np + n) + echelon_workspace_bytes(n, np + n));
+  cudaStream_t s = c.stream;
+  DView dC = c.ws.alloc(n, np + n);
+  zero_async(dC, s);
+  mzd_t *I = m4ri_b200_mzd_init(n, n);
+  for (rci_t i = 0; i < n; ++i) I->data[(int64_t)i * I->rowstride + i / 64] |= (word)1 << (i % 64);
+  upload(dC.sub(0, 0, n, n), A, s, &c.stager);
+  upload(dC.sub(0, np, n, np + n), I, s, &c.stager);
+  echelonize_device(dC, c.ws, s);
+  download(B, dC.sub(0, np, n, np + n), s, c.host_tmp, &c.stager);
+  M4B_CUDA(cudaStreamSynchronize(s));
+  m4ri_b200_mzd_free(I);
+  c.ws.release(0);
+  return B;
+}
+
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {
   if (A->nrows != B->nrows || A->ncols != B->ncols || C->nrows != A->nrows || C->ncols != A->ncols)
     die("m4ri_b200_dadd: dimension mismatch\n");

@@ -86,6 +86,7 @@ def _declare_ref(lib):
     lib.mzd_echelonize_m4ri.argtypes, lib.mzd_echelonize_m4ri.restype = [MzdP, c_int, c_int], c_int
     lib.mzd_echelonize_naive.argtypes, lib.mzd_echelonize_naive.restype = [MzdP, c_int], c_int
     lib.mzd_echelonize_pluq.argtypes, lib.mzd_echelonize_pluq.restype = [MzdP, c_int], c_int
+    lib.mzd_inv_m4ri.argtypes, lib.mzd_inv_m4ri.restype = [MzdP, MzdP, c_int], MzdP
     for name in ("mzd_trsm_lower_left", "mzd_trsm_upper_left", "mzd_trsm_lower_right", "mzd_trsm_upper_right"):
         getattr(lib, name).argtypes = [MzdP, MzdP, c_int]
         getattr(lib, name).restype = None
