@@ -9,6 +9,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "dev.h"
@@ -49,6 +50,12 @@ struct Ctx {
   char         last_path[64] = "none";
 };
 Ctx g;
+// The reference is "one host thread at a time" (SURVEY §8b), but an OpenMP libm4ri calls _mzd_mul_even /
+// _mzd_addmul_even from four concurrent sections (m4ri/mp.c:87-108, 206-227) and those calls bind here under
+// LD_PRELOAD: every entry point that touches the context (workspace stack, staging ring, streams) holds this
+// lock for its whole duration.  Recursive: mzd_mul_mp -> mzd_mul, m4ri_b200_inv_m4ri -> mzd_init helpers.
+std::recursive_mutex g_mu;
+#define M4B_LOCKED std::lock_guard<std::recursive_mutex> lock_(g_mu)
 unsigned long long g_products = 0;   // host-path products served (reported at exit with M4RI_B200_REPORT=1)
 
 void report_at_exit() {
@@ -262,6 +269,7 @@ struct HostOverlap : TopHooks {
 
 // The one host->device->host product path behind every reference-named entry point.
 void host_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool clear, bool strassen) {
+  M4B_LOCKED;
   Ctx &c = ctx();
   int const m = A->nrows, l = A->ncols, n = B->ncols;
   if (m == 0 || n == 0) return;
@@ -310,6 +318,7 @@ mzd_t *checked(char const *who, mzd_t *C, mzd_t const *A, mzd_t const *B) {
 // Host path of the triangular solves: T (t x t) and B (m x n) up, recursion on the device, X down into
 // B (only its valid bits).  left: T X = B (t == m), right: X T = B (t == n).
 void host_trsm(mzd_t const *T, mzd_t *B, int cutoff, bool upper, bool left) {
+  M4B_LOCKED;
   Ctx &c = ctx();
   int const m = B->nrows, n = B->ncols, t = T->nrows;
   if (m == 0 || n == 0) return;
@@ -339,6 +348,7 @@ DView as_view(m4ri_b200_dmat const *M) { return DView{M->data, M->pitch, M->nrow
 
 void device_product(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int levels, bool clear,
                     cudaStream_t s) {
+  M4B_LOCKED;
   Ctx &c = ctx();
   if (A->ncols != B->nrows || C->nrows != A->nrows || C->ncols != B->ncols)
     die("m4ri_b200_dmul: dimension mismatch (%dx%d) * (%dx%d) -> (%dx%d)\n", A->nrows, A->ncols, B->nrows, B->ncols,
@@ -449,6 +459,7 @@ M4B_TRSM_ENTRY(trsm_upper_right, true, false)
 
 // Row-blocks of C over the GPUs chosen with m4ri_b200_set_num_devices (multi.cu); one GPU: same as mzd_mul.
 mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  M4B_LOCKED;
   if (ctx().num_devices <= 1) return mzd_mul(C, A, B, cutoff);
   if (A->ncols != B->nrows) die("mzd_mul_mp: A ncols (%d) need to match B nrows (%d).\n", A->ncols, B->nrows);
   cutoff = norm_cutoff(cutoff, "mzd_mul_mp");
@@ -458,6 +469,7 @@ mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
 }
 
 mzd_t *mzd_addmul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  M4B_LOCKED;
   if (ctx().num_devices <= 1) return mzd_addmul(C, A, B, cutoff);
   if (A->ncols != B->nrows) die("mzd_addmul_mp: A ncols (%d) need to match B nrows (%d).\n", A->ncols, B->nrows);
   cutoff = norm_cutoff(cutoff, "mzd_addmul_mp");
@@ -478,7 +490,15 @@ int m4ri_b200_device_count(void) {
 }
 
 void m4ri_b200_set_device(int device) {
+  M4B_LOCKED;
   if (g.ready && g.device != device) {
+    // everything that belongs to the old device goes, on the old device: workspace, streams, the staging ring
+    // (its events were created there) and the leaf-profile event pool
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    cudaStreamSynchronize(g.copy_stream);
+    g.stager.release();
+    leaf_profile_reset();
     g.ws.destroy();
     cudaStreamDestroy(g.stream);
     cudaStreamDestroy(g.copy_stream);
@@ -492,6 +512,7 @@ void m4ri_b200_set_default_cutoff(int cutoff) { g.default_cutoff = cutoff > 0 ? 
 int  m4ri_b200_get_default_cutoff(void) { return g.default_cutoff ? g.default_cutoff : kBuiltinCutoff; }
 
 void m4ri_b200_release(void) {
+  M4B_LOCKED;
   multi_release();
   if (!g.ready) return;
   cudaStreamSynchronize(g.stream);
@@ -544,6 +565,7 @@ void m4ri_b200_mzd_free(mzd_t *M) {
 }
 
 m4ri_b200_dmat *m4ri_b200_dmat_alloc(rci_t nrows, rci_t ncols) {
+  M4B_LOCKED;
   ctx();
   m4ri_b200_dmat *M = static_cast<m4ri_b200_dmat *>(calloc(1, sizeof *M));
   M->nrows = nrows;
@@ -580,12 +602,14 @@ void m4ri_b200_dmat_free(m4ri_b200_dmat *M) {
 }
 
 void m4ri_b200_upload(m4ri_b200_dmat *dst, mzd_t const *src, void *stream) {
+  M4B_LOCKED;
   if (dst->nrows != src->nrows || dst->ncols != src->ncols) die("m4ri_b200_upload: dimension mismatch\n");
   upload(as_view(dst), src, stream ? static_cast<cudaStream_t>(stream) : ctx().stream, &ctx().stager);
   if (!stream) M4B_CUDA(cudaStreamSynchronize(ctx().stream));
 }
 
 void m4ri_b200_download(mzd_t *dst, m4ri_b200_dmat const *src, void *stream) {
+  M4B_LOCKED;
   if (dst->nrows != src->nrows || dst->ncols != src->ncols) die("m4ri_b200_download: dimension mismatch\n");
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
   download(dst, as_view(src), s, ctx().host_tmp, &ctx().stager);
@@ -615,6 +639,7 @@ void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200
 }
 
 void m4ri_b200_dtrsm(m4ri_b200_dmat const *T, m4ri_b200_dmat *B, int upper, int left, int cutoff, void *stream) {
+  M4B_LOCKED;
   if (T->nrows != T->ncols || (left ? T->ncols != B->nrows : T->nrows != B->ncols))
     die("m4ri_b200_dtrsm: dimension mismatch\n");
   Ctx &c = ctx();
@@ -627,6 +652,7 @@ void m4ri_b200_dtrsm(m4ri_b200_dmat const *T, m4ri_b200_dmat *B, int upper, int 
 }
 
 void m4ri_b200_dtranspose(m4ri_b200_dmat *DST, m4ri_b200_dmat const *A, void *stream) {
+  M4B_LOCKED;
   if (DST->nrows != A->ncols || DST->ncols != A->nrows) die("m4ri_b200_dtranspose: Wrong size for return matrix.\n");
   if (DST->data == A->data) die("m4ri_b200_dtranspose: DST must not alias A\n");
   launch_transpose(as_view(DST), as_view(A), stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
@@ -635,6 +661,7 @@ void m4ri_b200_dtranspose(m4ri_b200_dmat *DST, m4ri_b200_dmat const *A, void *st
 // Host form with the reference's semantics (mzd_transpose, m4ri/mzd.c:1118-1139): DST may be NULL
 // (allocated), wrong dimensions die, only DST's valid bits are written.
 mzd_t *m4ri_b200_transpose(mzd_t *DST, mzd_t const *A) {
+  M4B_LOCKED;
   if (DST == NULL) DST = alloc_result(A->ncols, A->nrows);
   else if (DST->nrows != A->ncols || DST->ncols != A->nrows) die("mzd_transpose: Wrong size for return matrix.\n");
   if (A->nrows == 0 || A->ncols == 0) return DST;
@@ -657,14 +684,16 @@ mzd_t *m4ri_b200_transpose(mzd_t *DST, mzd_t const *A) {
 // m4ri/brilliantrussian.c:603-967 — unique, so bit-identical); returns the rank.  full == 0 asks the reference for
 // *an* upper-triangular echelon form, which depends on its k; this library always returns the reduced one.
 int m4ri_b200_dechelonize(m4ri_b200_dmat *A, int full, void *stream) {
+  M4B_LOCKED;
   (void)full;
   Ctx &c = ctx();
   snprintf(c.last_path, sizeof c.last_path, "echelon");
-  c.ws.reserve(echelon_workspace_bytes(A->nrows, A->ncols));
+  c.ws.reserve(echelon_workspace_bytes(A->nrows, A->ncols, A->pitch));
   return echelonize_device(as_view(A), c.ws, stream ? static_cast<cudaStream_t>(stream) : c.stream);
 }
 
 rci_t m4ri_b200_echelonize(mzd_t *A, int full) {
+  M4B_LOCKED;
   (void)full;
   if (A->nrows == 0 || A->ncols == 0) return 0;
   Ctx &c = ctx();
@@ -686,6 +715,7 @@ rci_t m4ri_b200_echelonize(mzd_t *A, int full) {
 // reduced row echelon form of [A | 0 | I] (the identity starts at the next 128-column boundary).  Like the reference
 // it does not test invertibility: for a singular A the result is still that (unique) block.  B may be NULL.
 mzd_t *m4ri_b200_inv_m4ri(mzd_t *B, mzd_t const *A) {
+  M4B_LOCKED;
   if (A->nrows != A->ncols) die("mzd_inv_m4ri: the matrix must be square.\n");
   rci_t const n = A->nrows;
   if (B == NULL) B = alloc_result(n, n);
@@ -712,6 +742,7 @@ mzd_t *m4ri_b200_inv_m4ri(mzd_t *B, mzd_t const *A) {
 }
 
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {
+  M4B_LOCKED;
   if (A->nrows != B->nrows || A->ncols != B->ncols || C->nrows != A->nrows || C->ncols != A->ncols)
     die("m4ri_b200_dadd: dimension mismatch\n");
   launch_xor(as_view(C), as_view(A), as_view(B), stream ? static_cast<cudaStream_t>(stream) : ctx().stream);

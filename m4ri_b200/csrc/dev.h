@@ -55,6 +55,7 @@ extern int g_leaf_variant;
 extern int g_last_leaf;
 void leaf_profile_begin();
 unsigned long long leaf_profile_end(double *ms, double *bitops);
+void leaf_profile_reset();   // drop the event pool (its events belong to one device)
 
 // ---- element-wise helpers on views (all 128-bit vectorised) --------------------------
 void launch_xor(DView C, DView A, DView B, cudaStream_t stream);        // C = A ^ B
@@ -104,6 +105,6 @@ size_t trsm_workspace_bytes(int t, int m, int n, int cutoff);
 
 // ---- reduced row echelon form (echelon.cu) ----------------------------------------------------
 int    echelonize_device(DView A, Workspace &ws, cudaStream_t s);     // in place, returns the rank, synchronises s
-size_t echelon_workspace_bytes(int m, int n);
+size_t echelon_workspace_bytes(int m, int n, int64_t pitch_words = 0);   // pitch_words: A's pitch if above the minimal one
 
 }  // namespace m4b

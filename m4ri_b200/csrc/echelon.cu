@@ -78,9 +78,11 @@ size_t raw_bytes(size_t b) { return (b + 255) & ~(size_t)255; }
 
 }  // namespace
 
-size_t echelon_workspace_bytes(int m, int n) {
+size_t echelon_workspace_bytes(int m, int n, int64_t pitch_words) {
   int const nchunks = (m + chunk_rows_for(m) - 1) / chunk_rows_for(m);
-  size_t const pitch = (size_t)Workspace::pitch_for(n);
+  // PIV / Bm rows are as long as A's rows: a wrapped matrix may have a larger pitch than the minimal one
+  size_t const minimal = (size_t)Workspace::pitch_for(n);
+  size_t const pitch = pitch_words > (int64_t)minimal ? (size_t)pitch_words : minimal;
   return raw_bytes(sizeof(State)) + raw_bytes((size_t)nchunks * 64 * 4) + raw_bytes((size_t)nchunks * 64 * 8) +
          raw_bytes(128 * 8) + raw_bytes((size_t)m * 16) + 2 * raw_bytes(64 * pitch * 8) + 4096;
 }

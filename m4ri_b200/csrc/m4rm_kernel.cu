@@ -440,14 +440,23 @@ unsigned long long leaf_profile_end(double *ms, double *bitops) {
   return g_prof.used;
 }
 
-int m4rm_num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    M4B_CUDA(cudaGetDevice(&dev));
-    M4B_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+void leaf_profile_reset() {
+  for (auto &pr : g_prof.pool) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
   }
-  return sms;
+  g_prof.pool.clear();
+  g_prof.used = 0;
+  g_prof.on = false;
+}
+
+int m4rm_num_sms() {   // per device: the library may be pointed at another GPU (m4ri_b200_set_device, multi.cu)
+  static int sms[64] = {};
+  int dev = 0;
+  M4B_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!sms[dev]) M4B_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  return sms[dev];
 }
 
 // Leaf selection: M4RI_B200_LEAF=0|1|2 in the environment, or m4ri_b200_set_leaf_variant() at run time.

@@ -130,6 +130,8 @@ void Stager::download2d(void *dst, size_t dpitch, void const *src, size_t spitch
   auto issue = [&](size_t c) {
     int const slot = (int)(c % kSlots);
     size_t const r = c * rows_per_chunk, nr = rows - r < rows_per_chunk ? rows - r : rows_per_chunk;
+    // the slot may still be the source of an H2D copy that an earlier upload2d left in flight on another stream
+    M4B_CUDA(cudaEventSynchronize(done_[slot]));
     M4B_CUDA(cudaMemcpy2DAsync(slot_[slot], width, static_cast<char const *>(src) + r * spitch, spitch, width, nr,
                                cudaMemcpyDeviceToHost, s));
     M4B_CUDA(cudaEventRecord(done_[slot], s));

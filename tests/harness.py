@@ -162,6 +162,57 @@ def digest(M) -> str:
     return h.hexdigest()
 
 
+# ---- large seeded inputs (BASELINE configs 2-5): the same words here, in bench.py and in
+#      tests/golden/make_golden_large.py ------------------------------------------------------------
+
+SEED_A, SEED_B, SEED_C = 101, 102, 103
+
+
+def seeded_words(seed: int, nrows: int, width: int, row0: int = 0, nrows_total: int | None = None) -> np.ndarray:
+    """Rows row0 .. row0+nrows of the [nrows_total, width] uint64 matrix whose words are the raw 64-bit
+    outputs of numpy's PCG64(seed) in row-major order (one draw per word, so any row range can be
+    produced on its own by advancing the generator: ranks of a sharded run fill only their rows)."""
+    bg = np.random.PCG64(seed)
+    if row0:
+        bg.advance(row0 * width)
+    rng = np.random.Generator(bg)
+    out = np.empty((nrows, width), dtype=np.uint64)
+    step = max(1, (1 << 24) // max(1, width))
+    for i in range(0, nrows, step):
+        j = min(nrows, i + step)
+        out[i:j] = rng.integers(0, 2**64, size=(j - i, width), dtype=np.uint64)
+    return out
+
+
+def fill_seeded(M, seed: int) -> None:
+    """Fill a NON-window matrix with seeded_words(seed); excess bits cleared (mzd.h:117-122)."""
+    m = M.contents
+    st = storage(M)
+    st[:, :m.width] = seeded_words(seed, m.nrows, m.width)
+    st[:, m.width - 1] &= np.uint64(m.high_bitmask)
+    st[:, m.width:] = 0
+
+
+def block_digest(words2d: np.ndarray) -> str:
+    """sha256 of a contiguous copy of a [rows, words] block (shape first)"""
+    h = hashlib.sha256()
+    h.update(np.array(words2d.shape, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(words2d).tobytes())
+    return h.hexdigest()
+
+
+# C of every large case is recorded as 8 row-blocks x 2 column-blocks, so that every rank of a
+# 1/2/4/8-GPU partition (row-blocks, or pr x 2 grid) can check its own block against the reference.
+LARGE_BLOCK_ROWS, LARGE_BLOCK_COLS = 8, 2
+
+
+def large_block_digests(words2d: np.ndarray) -> list:
+    r, w = words2d.shape
+    br, bw = r // LARGE_BLOCK_ROWS, w // LARGE_BLOCK_COLS
+    return [[block_digest(words2d[i * br:(i + 1) * br, j * bw:(j + 1) * bw]) for j in range(LARGE_BLOCK_COLS)]
+            for i in range(LARGE_BLOCK_ROWS)]
+
+
 def equal(A, B) -> bool:
     return bool(oracle().orc_equal(A, B))
 
