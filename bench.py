@@ -1,21 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — GF(2) matmul bit-ops/s (2*n^3) at n = 65536 (BASELINE.json metric).
+"""bench.py — GF(2) matmul bit-ops/s (W = 2*m*l*n) on the BASELINE.json configurations.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 65536] [--cutoff 0]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload cfg3|cfg2|cfg5] [--size n] [--cutoff c]
 
-Own arm ("ours"):  one step = one mzd_mul of two random n x n GF(2) matrices (Strassen-Winograd
-over the M4RM leaf kernel, all on the GPU).
-  value      inputs already resident in HBM, timed with CUDA events on the launching stream,
-             max over ranks.
-  e2e        the same product through the reference-facing C-ABI call mzd_mul(C, A, B, cutoff)
-             with HOST (pinned) mzd_t operands: H2D of A and B and D2H of C inside the timed region.
-  roofline   the dominant kernel (m4rm_streamk_kernel) timed live with CUDA events around every
-             leaf launch of the timed region (library hook m4ri_b200_profile_*).
-  N > 1      C's row-blocks are sharded over the ranks (A row-block local, B row-slices
-             all-gathered over NCCL/NVLink every step), total work fixed -> "scaling": "strong".
-Reference arm ("--impl reference"): the unmodified reference (oracle/_ref/libm4ri_ref_omp.so,
-mzd_mul_mp with all host threads; serial mzd_mul if the OpenMP build is absent; the oracle port
-as last resort) on a bounded square sample of the same workload, rank 0 only.
+Workloads (BASELINE.json `configs`):
+  cfg3 (default)  mzd_mul 65536^3, Strassen-Winograd over the M4RM leaf; N > 1 is config 4 (C blocks over ranks)
+  cfg2            mzd_mul_m4rm 16384^3, the M4RM leaf kernel only (inputs fit the L2: flushed between steps)
+  cfg5            mzd_addmul 32768 x 131072 x 32768 into a random C
+Own arm ("ours"): one step = one product.
+  value      inputs already resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        the same product through the reference-facing C-ABI call on HOST mzd_t operands in PAGEABLE
+             memory (what mzd_init gives a libm4ri user), H2D and D2H inside the timed region;
+             e2e_pinned: the same from pinned host memory
+  roofline   the dominant kernel (M4RM leaf) timed live with CUDA events around every leaf launch
+  verified   after the timed legs: this rank's block of C against the sha256 digests of the unmodified
+             reference's result (tests/golden/large_golden.json, seeded inputs) + Freivalds on the device
+  N > 1      C is cut into pr x pc blocks over the ranks (m4ri_b200/shard.py); B's row-slices are
+             all-gathered over NCCL/NVLink every step; total work fixed -> "scaling": "strong"
+Reference arm ("--impl reference"): the unmodified reference (oracle/_ref/libm4ri_ref_omp.so, mzd_mul_mp /
+mzd_addmul_mp with all host threads) on a bounded sample of the same workload, rank 0 only.
 """
 import argparse
 import ctypes
@@ -34,6 +38,14 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gf2_matmul_bitops_per_s"
 UNIT = "bit-ops/s"
+L2_BYTES = 126 * 1000 * 1000
+
+WORKLOADS = {
+    #        kind      entry point        m       l       n      golden case                reference sample (m, l, n)
+    "cfg3": ("mul",    "mzd_mul",         65536,  65536,  65536, "cfg3_65536",              (32768, 32768, 32768)),
+    "cfg2": ("mul",    "mzd_mul_m4rm",    16384,  16384,  16384, "cfg2_16384",              (16384, 16384, 16384)),
+    "cfg5": ("addmul", "mzd_addmul",      32768, 131072,  32768, "cfg5_32768x131072x32768", (16384, 65536, 16384)),
+}
 
 
 def env_int(name, default):
@@ -41,6 +53,32 @@ def env_int(name, default):
         return int(os.environ.get(name, default))
     except ValueError:
         return default
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_of(args):
+    kind, fn, m, l, n, golden, sample = WORKLOADS[args.workload]
+    if args.n:
+        if args.workload == "cfg5":
+            raise SystemExit("--size applies to the square workloads")
+        m = l = n = args.n
+        sample = (min(args.n, sample[0]),) * 3
+    if args.ref_sample:
+        sample = (args.ref_sample,) * 3 if args.workload != "cfg5" else (args.ref_sample, 4 * args.ref_sample, args.ref_sample)
+    return kind, fn, m, l, n, golden, sample
+
+
+def workload_name(args, world):
+    kind, fn, m, l, n, _, _ = workload_of(args)
+    cfg = {"cfg3": "3" if world == 1 else "4", "cfg2": "2", "cfg5": "5"}[args.workload]
+    how = "M4RM leaf only" if fn == "mzd_mul_m4rm" else "Strassen-Winograd + M4RM leaf"
+    return f"{fn} {m}x{l}x{n} random GF(2), {how} (BASELINE config {cfg})"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -57,16 +95,6 @@ def make_header(MzdT, ptr, nrows, ncols, rowstride):
     h.high_bitmask = (1 << (ncols % 64)) - 1 if ncols % 64 else 2**64 - 1
     h.data = ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint64))
     return h
-
-
-def fill_random_words(arr_u64, seed):
-    """uniform random bits (density 1/2), deterministic per seed; chunked to bound temporaries"""
-    rng = np.random.default_rng(seed)
-    flat = arr_u64.reshape(-1)
-    step = 1 << 24
-    for i in range(0, flat.size, step):
-        j = min(flat.size, i + step)
-        flat[i:j] = rng.integers(0, 2**64, size=j - i, dtype=np.uint64)
 
 
 class ClockSampler:
@@ -132,44 +160,56 @@ def measured_peaks():
 # reference arm / cpu_baseline
 # ---------------------------------------------------------------------------------------------
 
-def time_reference(sample_n, runs, warm):
-    """Times the reference's own CPU multiply on sample_n^3 random inputs.
-    Returns (seconds per run, description dict)."""
+def time_reference(kind, dims, runs, warm):
+    """Times the reference's own CPU multiply (mzd_mul_mp / mzd_addmul_mp of the OpenMP build, every host
+    thread this process may use) on seeded random inputs of `dims`.  Returns (seconds per run, description)."""
+    threads = host_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to its children: the reference arm must not inherit that
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     from tests import harness as H
 
-    threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    lib, kind, fn_name, cores = None, "reference", "mzd_mul_mp", threads
+    m, l, n = dims
+    lib, what, fn_name, cores = None, "reference", "mzd_mul_mp" if kind == "mul" else "mzd_addmul_mp", threads
     if os.path.exists(H.REF_OMP_SO):
         lib = H.ref_omp()
+        try:   # libgomp may have been initialised (with the inherited value) before this point: set it explicitly
+            gomp = ctypes.CDLL("libgomp.so.1")
+            gomp.omp_set_num_threads(threads)
+            cores = int(gomp.omp_get_max_threads())
+        except OSError:
+            pass
     if lib is None and H.ref() is not None:
-        lib, fn_name, cores = H.ref(), "mzd_mul", 1
+        lib, fn_name, cores = H.ref(), "mzd_mul" if kind == "mul" else "mzd_addmul", 1
     if lib is not None:
-        A, B = lib.mzd_init(sample_n, sample_n), lib.mzd_init(sample_n, sample_n)
-        fn = getattr(lib, fn_name)
-        free = lib.mzd_free
+        A, B = lib.mzd_init(m, l), lib.mzd_init(l, n)
+        fn, free = getattr(lib, fn_name), lib.mzd_free
+        Cacc = lib.mzd_init(m, n) if kind == "addmul" else None
     else:  # neither reference build present: the oracle port (scalar, one thread)
         O = H.oracle()
-        kind, fn_name, cores = "port", "orc_mul", 1
-        A, B = O.orc_init(sample_n, sample_n), O.orc_init(sample_n, sample_n)
-        fn, free = O.orc_mul, O.orc_free
-    fill_random_words(H.storage(A), 101)
-    fill_random_words(H.storage(B), 102)
+        what, fn_name, cores = "port", "orc_mul" if kind == "mul" else "orc_addmul", 1
+        A, B = O.orc_init(m, l), O.orc_init(l, n)
+        fn, free = getattr(O, fn_name), O.orc_free
+        Cacc = O.orc_init(m, n) if kind == "addmul" else None
+    H.storage(A)[:, :A.contents.width] = H.seeded_words(H.SEED_A, m, A.contents.width)
+    H.storage(B)[:, :B.contents.width] = H.seeded_words(H.SEED_B, l, B.contents.width)
     times = []
     for i in range(warm + runs):
         t0 = time.perf_counter()
-        C = fn(None, A, B, 0)
+        C = fn(Cacc, A, B, 0)
         dt = time.perf_counter() - t0
-        free(C)
+        if Cacc is None:
+            free(C)
         if i >= warm:
             times.append(dt)
-    free(A)
-    free(B)
+    for M in (A, B, Cacc):
+        if M:
+            free(M)
     sec = sum(times) / len(times)
-    desc = {"kind": kind, "cores": cores,
-            "sample": f"{fn_name}(C, A, B, cutoff=0) on random {sample_n}^3 (1/{(65536 // sample_n) ** 3} of the "
-                      f"65536^3 workload's bit-ops; reference -O2 SSE2 build, {len(times)} timed run(s), "
-                      f"wall clock around the call as in bench/bench_multiplication.c:85-107)"}
+    desc = {"kind": what, "cores": cores,
+            "sample": f"{fn_name}(C, A, B, cutoff=0) on seeded random {m}x{l}x{n} "
+                      f"(reference -O2 SSE2 OpenMP build, {len(times)} timed run(s) after {warm} warm-up, wall clock "
+                      f"around the call as in bench/bench_multiplication.c:85-107)",
+            "sample_dims": [m, l, n], "sample_seconds": sec}
     return sec, desc
 
 
@@ -177,16 +217,20 @@ def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return  # other ranks exit 0 without work
-    total = args.steps + args.warmup
-    sample_n = 32768 if total <= 6 else 16384
-    sec, desc = time_reference(sample_n, args.steps, args.warmup)
-    value = 2.0 * sample_n ** 3 / sec
+    kind, fn, m, l, n, _, sample = workload_of(args)
+    sec, desc = time_reference(kind, sample, args.steps, args.warmup)
+    value = 2.0 * sample[0] * sample[1] * sample[2] / sec
+    same = list(sample) == [m, l, n]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"mzd_mul {args.n}x{args.n}x{args.n} random GF(2) (BASELINE config 3); "
-                               f"CPU arm timed on a bounded {sample_n}^3 sample", "sample_n": sample_n},
+        "config": {"workload": workload_name(args, 1) +
+                               ("" if same else f"; CPU arm timed on a bounded {sample[0]}x{sample[1]}x{sample[2]} sample "
+                                                "(1/%d of the bit-ops; the reference's nominal rate grows with n — "
+                                                "profiles/r02_reference_full_size.json holds a full-size run)"
+                                                % round(m * l * n / (sample[0] * sample[1] * sample[2]))),
+                   "sample_dims": list(sample), "same_size_as_workload": same},
         "cpu_baseline": dict(desc, value=value, unit=UNIT),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -203,7 +247,8 @@ def run_own_arm(args):
     import torch.distributed as dist
 
     import m4ri_b200
-    from m4ri_b200 import MzdT
+    from m4ri_b200 import MzdT, shard
+    from tests import harness as H     # seeded input generator + digest helpers (no oracle call on this path)
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world != args.gpus:
@@ -218,20 +263,21 @@ def run_own_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    n = args.n
-    if n % (128 * world):
-        raise SystemExit("n must be a multiple of 128 * gpus")
+    kind, fn_name, m, l, n, golden_name, _ = workload_of(args)
+    accumulate = kind == "addmul"
+    leaf_only = fn_name == "mzd_mul_m4rm"
+    if m % (128 * world) or l % (128 * world) or n % (128 * world):
+        raise SystemExit("m, l, n must be multiples of 128 * gpus")
     cutoff = args.cutoff
-    from m4ri_b200 import shard
     # C is cut into pr row-blocks x pc column-blocks (pc = 2 from 4 ranks on, see m4ri_b200/shard.py):
     # this rank owns C[rows gr, cols gc] = A[rows gr, :] * B[:, cols gc]
     pr, pc = shard.grid_shape(world, args.grid)
     gr, gc = shard.grid_coords(rank, world, args.grid)
-    r0, r1 = shard.row_blocks(n, pr)[gr]
+    r0, r1 = shard.row_blocks(m, pr)[gr]
     c0, c1 = shard.col_blocks(n, pc)[gc]
-    rows, ncb = r1 - r0, c1 - c0           # this rank's block of C; A block is rows x n, B block n x ncb
-    brow = shard.padded_slice_rows(n, pr)  # this rank's row-slice of B[:, cols gc] (n % (64*world) == 0: no padding)
-    pitch, pitchb = n // 64, ncb // 64
+    rows, ncb = r1 - r0, c1 - c0           # this rank's block of C; A block is rows x l, B block l x ncb
+    brow = shard.padded_slice_rows(l, pr)  # this rank's row-slice of B[:, cols gc] (l % (64*world) == 0: no padding)
+    pitch, pitchb = l // 64, ncb // 64
     group = None
     if world > 1 and pc > 1:               # every rank creates every column group, in the same order
         groups = [dist.new_group(shard.column_group(g, world, args.grid)) for g in range(pc)]
@@ -241,47 +287,84 @@ def run_own_arm(args):
     torch.cuda.set_stream(tstream)
     sh = ctypes.c_void_p(tstream.cuda_stream)
 
-    # ---- host inputs (pinned): A row-block, B piece, C block -------------------------------------
-    pin = not args.pageable
-    hA = torch.empty((rows, pitch), dtype=torch.int64, pin_memory=pin)
-    hB = torch.empty((brow, pitchb), dtype=torch.int64, pin_memory=pin)
-    hC = torch.zeros((rows, pitchb), dtype=torch.int64, pin_memory=pin)
-    fill_random_words(hA.numpy().view(np.uint64), 1000 + gr)          # ranks of one row-block share A's rows
-    fill_random_words(hB.numpy().view(np.uint64), 2000 + rank)
-    mA = make_header(MzdT, hA.data_ptr(), rows, n, pitch)
-    mB = make_header(MzdT, hB.data_ptr(), brow, ncb, pitchb)
-    mC = make_header(MzdT, hC.data_ptr(), rows, ncb, pitchb)
+    # ---- host inputs: this rank's rows of the SEEDED global matrices (tests/harness.py: the generator the golden
+    #      digests were made with), once in pageable and once in pinned memory -------------------------------------
+    wc0, wc1 = c0 // 64, c1 // 64
+    srcA = H.seeded_words(H.SEED_A, rows, pitch, row0=r0)
+    srcB = np.ascontiguousarray(H.seeded_words(H.SEED_B, brow, n // 64, row0=gr * brow)[:, wc0:wc1])
+    srcC = np.ascontiguousarray(H.seeded_words(H.SEED_C, rows, n // 64, row0=r0)[:, wc0:wc1]) if accumulate else None
+
+    class HostSet:
+        def __init__(self, pinned):
+            self.pinned = pinned
+            if pinned:
+                self.tA = torch.empty((rows, pitch), dtype=torch.int64, pin_memory=True)
+                self.tB = torch.empty((brow, pitchb), dtype=torch.int64, pin_memory=True)
+                self.tC = torch.zeros((rows, pitchb), dtype=torch.int64, pin_memory=True)
+                self.A, self.B, self.C = (t.numpy().view(np.uint64) for t in (self.tA, self.tB, self.tC))
+            else:   # plain (malloc/mmap) memory, as mzd_init gives it
+                self.A = np.empty((rows, pitch), dtype=np.uint64)
+                self.B = np.empty((brow, pitchb), dtype=np.uint64)
+                self.C = np.zeros((rows, pitchb), dtype=np.uint64)
+            self.A[:, :] = srcA
+            self.B[:, :] = srcB
+            self.reset_c()
+            self.mA = make_header(MzdT, self.A.ctypes.data, rows, l, pitch)
+            self.mB = make_header(MzdT, self.B.ctypes.data, brow, ncb, pitchb)
+            self.mC = make_header(MzdT, self.C.ctypes.data, rows, ncb, pitchb)
+
+        def reset_c(self):
+            if accumulate:
+                self.C[:, :] = srcC
+            else:
+                self.C[:, :] = 0
+
+    kinds = []
+    if not args.no_e2e:
+        kinds = ["pageable", "pinned"] if not (args.pageable or args.pinned) else (["pageable"] if args.pageable else ["pinned"])
+    hosts = {k: HostSet(k == "pinned") for k in kinds}
+    upload_from = hosts[kinds[0]] if kinds else HostSet(False)
 
     # ---- device matrices (torch owns the memory; the library sees plain pointers) --------------
     tA = torch.zeros((rows, pitch), dtype=torch.int64, device="cuda")
     tBs = torch.zeros((brow, pitchb), dtype=torch.int64, device="cuda")
-    tB = tBs if pr == 1 else torch.zeros((n, pitchb), dtype=torch.int64, device="cuda")
+    tB = tBs if pr == 1 else torch.zeros((l, pitchb), dtype=torch.int64, device="cuda")
     tC = torch.zeros((rows, pitchb), dtype=torch.int64, device="cuda")
-    dA = lib.m4ri_b200_dmat_wrap(tA.data_ptr(), pitch, rows, n)
+    dA = lib.m4ri_b200_dmat_wrap(tA.data_ptr(), pitch, rows, l)
     dBs = lib.m4ri_b200_dmat_wrap(tBs.data_ptr(), pitchb, brow, ncb)
-    dB = lib.m4ri_b200_dmat_wrap(tB.data_ptr(), pitchb, n, ncb)
+    dB = lib.m4ri_b200_dmat_wrap(tB.data_ptr(), pitchb, l, ncb)
     dC = lib.m4ri_b200_dmat_wrap(tC.data_ptr(), pitchb, rows, ncb)
-    lib.m4ri_b200_upload(dA, ctypes.byref(mA), sh)
-    lib.m4ri_b200_upload(dBs, ctypes.byref(mB), sh)
+    lib.m4ri_b200_upload(dA, ctypes.byref(upload_from.mA), sh)
+    lib.m4ri_b200_upload(dBs, ctypes.byref(upload_from.mB), sh)
+    if accumulate:
+        lib.m4ri_b200_upload(dC, ctypes.byref(upload_from.mC), sh)
     torch.cuda.synchronize()
 
     def exchange():
         if pr > 1:  # the path's one exchange step: all-gather of the row-slices of B[:, cols gc] over NVLink
             dist.all_gather_into_tensor(tB.view(-1), tBs.view(-1), group=group)
 
+    def device_product():
+        if leaf_only:
+            lib.m4ri_b200_dmul_m4rm(dC, dA, dB, 0 if accumulate else 1, sh)
+        else:
+            lib.m4ri_b200_dmul(dC, dA, dB, cutoff, 0 if accumulate else 1, sh)
+
     def step_resident():
         exchange()
-        lib.m4ri_b200_dmul(dC, dA, dB, cutoff, 1, sh)
+        device_product()
 
-    def step_e2e():
-        if world == 1:
-            lib.mzd_mul(ctypes.byref(mC), ctypes.byref(mA), ctypes.byref(mB), cutoff)   # the drop-in call
+    def step_e2e(hs):
+        if world == 1:   # the drop-in call itself
+            getattr(lib, fn_name)(ctypes.byref(hs.mC), ctypes.byref(hs.mA), ctypes.byref(hs.mB), cutoff)
         else:
-            lib.m4ri_b200_upload(dA, ctypes.byref(mA), sh)
-            lib.m4ri_b200_upload(dBs, ctypes.byref(mB), sh)
+            lib.m4ri_b200_upload(dA, ctypes.byref(hs.mA), sh)
+            lib.m4ri_b200_upload(dBs, ctypes.byref(hs.mB), sh)
+            if accumulate:
+                lib.m4ri_b200_upload(dC, ctypes.byref(hs.mC), sh)
             exchange()
-            lib.m4ri_b200_dmul(dC, dA, dB, cutoff, 1, sh)
-            lib.m4ri_b200_download(ctypes.byref(mC), dC, sh)
+            device_product()
+            lib.m4ri_b200_download(ctypes.byref(hs.mC), dC, sh)
 
     def barrier():
         if world > 1:
@@ -295,6 +378,17 @@ def run_own_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks_ok(ok):
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    # inputs smaller than twice the L2 would be served from it on a repeat: flush between steps (cfg2)
+    resident_bytes = (rows * pitch + l * pitchb + rows * pitchb) * 8
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if resident_bytes < 2 * L2_BYTES else None
+
     # ---- resident-input timing ------------------------------------------------------------------
     for _ in range(args.warmup):
         step_resident()
@@ -304,56 +398,89 @@ def run_own_arm(args):
         sampler.start()
     launches0 = lib.m4ri_b200_kernel_launches()
     lib.m4ri_b200_profile_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        step_resident()
-    e1.record()
-    barrier()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_resident()
+        e1.record()
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+    else:
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_resident()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
     wall1 = time.time()
     leaf_ms, leaf_bitops = ctypes.c_double(0), ctypes.c_double(0)
     leaf_launches = lib.m4ri_b200_profile_end(ctypes.byref(leaf_ms), ctypes.byref(leaf_bitops))
     launches = lib.m4ri_b200_kernel_launches() - launches0
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    ms_step = max_over_ranks(total_ms / args.steps)
     path = lib.m4ri_b200_last_path().decode()
-    total_bitops = 2.0 * n * n * n
+    total_bitops = 2.0 * m * l * n
     value = total_bitops / (ms_step * 1e-3)
 
     # ---- end-to-end timing (host buffers in, host buffer out) ------------------------------------
-    if args.no_e2e:
-        e2e_s = float("nan")
-    else:
+    e2e = {}
+    h2d = (rows * pitch + brow * pitchb + (rows * pitchb if accumulate else 0)) * 8 * world
+    d2h = rows * pitchb * 8 * world
+    for k in kinds:
+        hs = hosts[k]
         for _ in range(min(args.warmup, 2)):
-            step_e2e()
+            step_e2e(hs)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            step_e2e()
+            step_e2e(hs)
         barrier()
-        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    e2e_value = total_bitops / e2e_s
-    h2d = (rows * pitch + brow * pitchb) * 8 * world
-    d2h = rows * pitchb * 8 * world
+        sec = max_over_ranks((time.perf_counter() - t0) / args.steps)
+        e2e[k] = {"value": total_bitops / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": d2h, "host_memory": k,
+                  "api": f"{fn_name}(C, A, B, cutoff) on host mzd_t" if world == 1 else
+                  "upload + all_gather + m4ri_b200_dmul + download per rank"}
 
-    if args.verify:   # small-n correctness of this rank's block against the oracle (never at full size)
-        from tests import harness as H
-        step_e2e()
-        col_b = torch.empty((n, pitchb), dtype=torch.int64)
-        col_b.copy_(tB)
-        Ao, Bo = H.new(rows, n), H.new(n, ncb)
-        H.storage(Ao)[:, :] = hA.numpy().view(np.uint64)
-        H.storage(Bo)[:, :] = col_b.numpy().view(np.uint64)
-        want = H.oracle().orc_mul(None, Ao, Bo, 0)
-        ok = bool(np.array_equal(H.storage(want), hC.numpy().view(np.uint64)))
-        print(f"[verify] rank {rank}: rows {r0}:{r1} cols {c0}:{c1} {'OK' if ok else 'MISMATCH'}", file=sys.stderr, flush=True)
-        if not ok:
-            raise SystemExit(3)
-
-    if args.check:    # any size, on the device: the exchange delivered the pieces in order, and Freivalds on this
-        #               rank's block with 128 random vectors: C_blk * X == A_blk * (B_colblk * X)   (error 2^-128)
+    # ---- verification (after the timed legs; default on) -------------------------------------------------
+    verified = None
+    if not args.no_check:
+        verified = {}
+        # (1) bit-exact against the unmodified reference: digests of its result blocks for the same seeded inputs
+        digest_ok = None
+        gpath = os.path.join(ROOT, "tests", "golden", "large_golden.json")
+        case = None
+        if os.path.exists(gpath):
+            with open(gpath) as f:
+                case = json.load(f)["cases"].get(golden_name)
+            if case and (case["m"], case["l"], case["n"]) != (m, l, n):
+                case = None
+        if case is not None and kinds:
+            hs = hosts[kinds[0]]
+            hs.reset_c()
+            step_e2e(hs)
+            torch.cuda.synchronize()
+            br, bw = m // H.LARGE_BLOCK_ROWS, (n // 64) // H.LARGE_BLOCK_COLS
+            digest_ok = rows % br == 0 and (pitchb % bw == 0)
+            if digest_ok:
+                for i in range(rows // br):
+                    for j in range(pitchb // bw):
+                        got = H.block_digest(hs.C[i * br:(i + 1) * br, j * bw:(j + 1) * bw])
+                        digest_ok = digest_ok and got == case["C_blocks"][r0 // br + i][wc0 // bw + j]
+            digest_ok = all_ranks_ok(digest_ok)
+        verified["reference_digest"] = digest_ok
+        verified["reference_digest_source"] = ("tests/golden/large_golden.json:" + golden_name) if case is not None else None
+        # (2) on the device, any size: the exchange delivered the pieces in order, and Freivalds on this rank's block
+        #     with 128 random vectors: C_blk * X == A_blk * (B_colblk * X) [^ C_in * X]   (error probability 2^-128)
+        if accumulate:
+            upload_from.reset_c()
+            lib.m4ri_b200_upload(dC, ctypes.byref(upload_from.mC), sh)
         step_resident()
         torch.cuda.synchronize()
         ok = True
@@ -363,18 +490,43 @@ def run_own_arm(args):
             dist.all_gather_into_tensor(sums, mine, group=group)
             ok = bool(torch.equal(tB.view(pr, brow, pitchb).sum(dim=(1, 2)), sums))
         tX = torch.randint(-2**62, 2**62, (ncb, 2), dtype=torch.int64, device="cuda")
-        tY = torch.zeros((n, 2), dtype=torch.int64, device="cuda")
+        tY = torch.zeros((l, 2), dtype=torch.int64, device="cuda")
         tZ = torch.zeros((rows, 2), dtype=torch.int64, device="cuda")
         tW = torch.zeros((rows, 2), dtype=torch.int64, device="cuda")
-        dX, dY = lib.m4ri_b200_dmat_wrap(tX.data_ptr(), 2, ncb, 128), lib.m4ri_b200_dmat_wrap(tY.data_ptr(), 2, n, 128)
+        dX, dY = lib.m4ri_b200_dmat_wrap(tX.data_ptr(), 2, ncb, 128), lib.m4ri_b200_dmat_wrap(tY.data_ptr(), 2, l, 128)
         dZ, dW = lib.m4ri_b200_dmat_wrap(tZ.data_ptr(), 2, rows, 128), lib.m4ri_b200_dmat_wrap(tW.data_ptr(), 2, rows, 128)
         torch.cuda.synchronize()
         lib.m4ri_b200_dmul_m4rm(dY, dB, dX, 1, sh)
         lib.m4ri_b200_dmul_m4rm(dZ, dA, dY, 1, sh)
+        if accumulate:   # Z = A (B X) ^ C_in X
+            tCin = torch.from_numpy(srcC.view(np.int64)).to("cuda")
+            dCin = lib.m4ri_b200_dmat_wrap(tCin.data_ptr(), pitchb, rows, ncb)
+            torch.cuda.synchronize()
+            lib.m4ri_b200_dmul_m4rm(dZ, dCin, dX, 0, sh)
         lib.m4ri_b200_dmul_m4rm(dW, dC, dX, 1, sh)
         torch.cuda.synchronize()
         ok = ok and bool(torch.equal(tZ, tW)) and bool(tZ.any())
-        print(f"[check] rank {rank}: rows {r0}:{r1} cols {c0}:{c1} {'OK' if ok else 'MISMATCH'}", file=sys.stderr, flush=True)
+        verified["freivalds"] = all_ranks_ok(ok)
+        verified["freivalds_vectors"] = 128
+        print(f"[check] rank {rank}: rows {r0}:{r1} cols {c0}:{c1} digest={digest_ok} freivalds={ok}", file=sys.stderr, flush=True)
+        if verified["freivalds"] is False or verified["reference_digest"] is False:
+            print(json.dumps({"error": "verification failed", "verified": verified}), flush=True)
+            raise SystemExit(3)
+
+    if args.verify:   # small-n correctness of this rank's block against the oracle (never at full size)
+        hs = hosts[kinds[0]]
+        hs.reset_c()
+        step_e2e(hs)
+        col_b = torch.empty((l, pitchb), dtype=torch.int64)
+        col_b.copy_(tB)
+        Ao, Bo, Co = H.new(rows, l), H.new(l, ncb), H.new(rows, ncb)
+        H.storage(Ao)[:, :] = hs.A
+        H.storage(Bo)[:, :] = col_b.numpy().view(np.uint64)
+        if accumulate:
+            H.storage(Co)[:, :] = srcC
+        want = H.oracle().orc_addmul(Co, Ao, Bo, 0)
+        ok = bool(np.array_equal(H.storage(want), hs.C))
+        print(f"[verify] rank {rank}: rows {r0}:{r1} cols {c0}:{c1} {'OK' if ok else 'MISMATCH'}", file=sys.stderr, flush=True)
         if not ok:
             raise SystemExit(3)
 
@@ -396,14 +548,16 @@ def run_own_arm(args):
     leaf_variant = lib.m4ri_b200_last_leaf_variant()
     if leaf_variant == 2:
         smem_bytes_per_bitop = (4096 * 8 * 16 + 2048 * 16 + 4096 * 4 + 32 * 32) / (2.0 * 32 * 4096 * 256)
+        lookup_bytes_per_bitop = (4096 * 8 * 16) / (2.0 * 32 * 4096 * 256)
     else:
         smem_bytes_per_bitop = (1024 * 2 * 128 + 512 * 128 + 1024 * 2 + 16 * 128) / (2.0 * 16 * 1024 * 1024)
+        lookup_bytes_per_bitop = (1024 * 2 * 128) / (2.0 * 16 * 1024 * 1024)
     smem_peak_gbs = 128.0 * 148 * sm_max_mhz * 1e6 / 1e9
     smem_achieved_gbs = leaf_rate * smem_bytes_per_bitop / 1e9
     leaf_dims = None
     try:
         lv = int(path.split(":")[1]) if ":" in path else 0
-        leaf_dims = (rows >> lv, n >> lv, ncb >> lv)
+        leaf_dims = (rows >> lv, l >> lv, ncb >> lv)
     except ValueError:
         lv = 0
     # compulsory HBM bytes of one leaf launch: read A and B once, RMW C once
@@ -428,6 +582,8 @@ def run_own_arm(args):
         "kernel": "m4rm_leaf2_kernel" if leaf_variant == 2 else "m4rm_streamk_kernel", "bound": "smem", "unit": "GB/s",
         "algorithmic_smem_bytes_per_bitop": smem_bytes_per_bitop,
         "achieved": smem_achieved_gbs, "peak": smem_peak_gbs, "frac": smem_achieved_gbs / smem_peak_gbs,
+        # SURVEY §8d's own roof counts the table LOOKUPS only (16*k*128 B/clk/SM at k = 8): the stricter fraction
+        "frac_lookup_only": leaf_rate * lookup_bytes_per_bitop / 1e9 / smem_peak_gbs,
         "peak_source": f"128 B/clk/SM x 148 SMs x {sm_max_mhz:.0f} MHz (clocks.max.sm, {peak_src})",
         "traffic": traffic,
         "leaf_launches": int(leaf_launches), "leaf_avg_ms": leaf_avg_ms, "leaf_dims": leaf_dims,
@@ -438,9 +594,9 @@ def run_own_arm(args):
                 "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src},
     }
 
-    # ---- the HBM-bound kernel of the path: the device _mzd_add (C = A ^ B) on the full operands ----------
+    # ---- the HBM-bound kernel of the path: the device _mzd_add (C = A ^ B) on square operands ----------
     add_roofline = None
-    if world == 1:
+    if world == 1 and m == l == n:
         for _ in range(3):
             lib.m4ri_b200_dadd(dC, dA, dB, sh)
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -454,32 +610,36 @@ def run_own_arm(args):
         add_gbs = add_bytes / (add_ms * 1e-3) / 1e9
         add_roofline = {"kernel": "ew_kernel<0> (_mzd_add)", "bound": "hbm", "unit": "GB/s", "achieved": add_gbs,
                         "peak": hbm_peak, "frac": add_gbs / hbm_peak, "ms": add_ms,
-                        "algorithmic_bytes_per_launch": add_bytes, "peak_source": peak_src}
+                        "algorithmic_bytes_per_launch": add_bytes, "peak_source": peak_src,
+                        "note": "operands in L2 at this size" if add_bytes < 2 * L2_BYTES else None}
 
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sec, desc = time_reference(16384, 3, 1)
-        cpu = dict(desc, value=2.0 * 16384 ** 3 / sec, unit=UNIT)
+        sample = workload_of(args)[6]
+        sec, desc = time_reference(kind, sample, 2, 1)
+        cpu = dict(desc, value=2.0 * sample[0] * sample[1] * sample[2] / sec, unit=UNIT)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"mzd_mul {n}x{n}x{n} random GF(2), Strassen-Winograd + M4RM leaf (BASELINE config "
-                               f"{'3' if world == 1 else '4'})", "n": n, "cutoff": cutoff or lib.m4ri_b200_get_default_cutoff(),
-                   "path": path,
+        "config": {"workload": workload_name(args, world), "dims": [m, l, n],
+                   "cutoff": cutoff or lib.m4ri_b200_get_default_cutoff(), "path": path,
                    "parallelism": (f"row-block x{world}" if pc == 1 else f"C blocks {pr} x {pc} (row-blocks x column-blocks)") +
                                   ("" if world == 1 else ", NCCL all-gather of B per step" if pc == 1 else
                                    f", NCCL all-gather of B's column block inside each column group ({pr} ranks) per step"),
-                   "local_product": [rows, n, ncb],
-                   "l2": "inputs (3 x %d MiB) exceed the 126 MB L2; no flush needed" % (n * n // 8 >> 20)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "host_memory": "pageable" if args.pageable else "pinned",
-                "api": "mzd_mul(C, A, B, cutoff) on host mzd_t" if world == 1 else
-                "upload + all_gather + m4ri_b200_dmul + download per rank"},
+                   "local_product": [rows, l, ncb],
+                   "l2": ("inputs (%d MiB per rank) exceed the 126 MB L2; no flush needed" % (resident_bytes >> 20)) if flush is None
+                         else "inputs fit the L2: a 256 MiB buffer is written between timed steps, steps timed one by one"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
     }
+    if kinds:
+        line["e2e"] = e2e[kinds[0]]
+        for k in kinds[1:]:
+            line["e2e_" + k] = e2e[k]
+    if verified is not None:
+        line["verified"] = verified
     if add_roofline is not None:
         line["roofline_add"] = add_roofline
     if cpu is not None:
@@ -495,15 +655,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", dest="n", type=int, default=65536, help="n of the n x n x n product")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--size", dest="n", type=int, default=0, help="n of an n x n x n product instead of the workload's size")
     ap.add_argument("--cutoff", type=int, default=0)
+    ap.add_argument("--ref-sample", type=int, default=0, help="reference arm / cpu_baseline: sample size (default 32768 for cfg3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
-    ap.add_argument("--pageable", action="store_true", help="e2e with pageable (malloc) host matrices instead of pinned")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end legs (profiling runs)")
+    ap.add_argument("--pageable", action="store_true", help="only the pageable end-to-end leg")
+    ap.add_argument("--pinned", action="store_true", help="only the pinned end-to-end leg")
     ap.add_argument("--grid", default="auto", choices=["auto", "rows"],
                     help="C partition over ranks: 'rows' = row-blocks only; 'auto' = two column blocks from 4 ranks on")
-    ap.add_argument("--check", action="store_true", help="device-side check at any size: exchange order + Freivalds on this rank's block")
-    ap.add_argument("--verify", action="store_true", help="check this rank's C block against the oracle (small --n only)")
+    ap.add_argument("--no-check", action="store_true", help="skip the verification after the timed legs")
+    ap.add_argument("--verify", action="store_true", help="check this rank's C block against the oracle (small --size only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

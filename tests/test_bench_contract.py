@@ -12,9 +12,9 @@ REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_
 
 
 def test_reference_arm_prints_one_valid_json_line():
-    env = dict(os.environ, OMP_NUM_THREADS=str(min(8, os.cpu_count() or 1)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")   # as under torch.distributed.run
     p = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
-                        "--steps", "6", "--warmup", "1"], capture_output=True, text=True, timeout=900, env=env)
+                        "--steps", "3", "--warmup", "1", "--ref-sample", "8192"], capture_output=True, text=True, timeout=900, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -25,6 +25,8 @@ def test_reference_arm_prints_one_valid_json_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"]
+    # torchrun exports OMP_NUM_THREADS=1; the arm must still use every host thread it may run on
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) or d["cpu_baseline"]["kind"] != "reference"
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
