@@ -86,3 +86,76 @@ def sharded_product_2d(rank: int, world: int, a_block, b_piece, group_all_gather
     """
     b_col = group_all_gather(b_piece, column_group(rank, world, mode))
     return local_mul(a_block, b_col)
+
+
+# ---- K-chunk pipeline of the end-to-end path (host <-> device transfers overlapped with compute) ------------
+#
+# C_blk = XOR over K-chunks of A[rows gr, K_c] * B[K_c, cols gc] is exact in any order, so a rank
+# can start multiplying as soon as ONE chunk of its operands is on the device and keep the PCIe link busy with
+# the next chunks meanwhile.  The K range is cut into pr * sub chunks: chunk (g, j) is sub-chunk j of the
+# row-slice of B that rank (g, gc) contributes to its column group.  A rank's own slice needs no exchange, so it
+# goes first; the other slices follow in rotated order.  PCIe carries every operand bit exactly once per node:
+# the pc ranks of a row group each upload 1/pc of the rows of an A chunk and all-gather the parts over NVLink
+# (row group), just as the pr ranks of a column group do for B.  The last chunk's product is cut into row parts
+# so that the download of one part overlaps the product of the next.
+
+def row_group(rank: int, world: int, mode: str = "auto") -> List[int]:
+    """The ranks that share this rank's row-block of A and C, in column-block order (= gather order)."""
+    _, pc = grid_shape(world, mode)
+    gr = rank // pc
+    return [gr * pc + gc for gc in range(pc)]
+
+
+def chunk_schedule(gr: int, pr: int, sub: int = 1) -> List[Tuple[int, int]]:
+    """Order in which rank (gr, *) consumes the K-chunks (g, j): its own slice first, then g = gr+1, ... (mod pr)."""
+    return [((gr + d) % pr, j) for d in range(pr) for j in range(sub)]
+
+
+def chunk_range(l: int, pr: int, sub: int, g: int, j: int, align: int = 128) -> Tuple[int, int]:
+    """[k0, k1) of K-chunk (g, j); the chunk size must be a multiple of `align` bits (device views and TMA boxes)."""
+    if l % (pr * sub * align):
+        raise ValueError(f"l = {l} is not a multiple of {pr * sub * align}")
+    kc = l // (pr * sub)
+    k0 = (g * sub + j) * kc
+    return k0, k0 + kc
+
+
+def pipelined_product(rank: int, world: int, ops, sub: int = 1, mode: str = "auto", tail_parts: int = 2,
+                      accumulate: bool = False) -> None:
+    """One end-to-end step on this rank.  `ops` supplies the transfers, exchanges and products (all asynchronous
+    on the caller's streams; bench.py on the GPU, numpy + gloo in the CPU tests):
+
+      upload_c()                 C block (accumulate only)
+      upload_b(j)                this rank's sub-chunk j of its B row-slice          -> device
+      gather_b(j)                all-gather of sub-chunk j inside the column group   (collective, column group)
+      upload_a(g, j)             this rank's 1/pc row part of A chunk (g, j)         -> device
+      gather_a(g, j)             all-gather of the parts inside the row group        (collective, row group; pc > 1)
+      mul(g, j, clear, part)     C[part] (^)= A[part rows, K(g,j)] * B[K(g,j), :]    part = None (all rows) or (i, nparts)
+      download(part)             C[part] -> host (waits for the last product of that part only)
+
+    Every rank issues its collectives in the same relative order (position p of every rank's sequence is the same
+    collective on the same communicator), so the schedule cannot deadlock."""
+    pr, pc = grid_shape(world, mode)
+    gr, _ = grid_coords(rank, world, mode)
+    sched = chunk_schedule(gr, pr, sub)
+    if accumulate:
+        ops.upload_c()
+    for idx, (g, j) in enumerate(sched):
+        own = g == gr
+        if own:
+            ops.upload_b(j)
+        ops.upload_a(g, j)
+        if pc > 1:
+            ops.gather_a(g, j)
+        clear = idx == 0 and not accumulate
+        if idx + 1 < len(sched):
+            ops.mul(g, j, clear, None)
+        else:
+            for i in range(tail_parts):
+                ops.mul(g, j, clear, (i, tail_parts))
+        if own and pr > 1:
+            ops.gather_b(j)          # after the own product: it must not wait for the slowest peer's upload
+    # downloads are issued after every product has been enqueued: a device->host copy blocks the calling thread
+    # until its part is final, and the parts that follow must already be running behind it
+    for i in range(tail_parts):
+        ops.download((i, tail_parts))

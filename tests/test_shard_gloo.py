@@ -171,3 +171,121 @@ def test_grid_product_over_gloo(world, shape):
         p.join(240)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+# ---- K-chunk pipeline (end-to-end path of bench.py --gpus N): schedule + exchanges over gloo ------------------
+
+def test_chunk_schedule_and_groups():
+    assert shard.chunk_schedule(1, 4, 2) == [(1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1), (0, 0), (0, 1)]
+    assert shard.chunk_schedule(0, 2) == [(0, 0), (1, 0)]
+    for world in (2, 4, 8):
+        pr, pc = shard.grid_shape(world)
+        for rank in range(world):
+            grp = shard.row_group(rank, world)
+            assert rank in grp and len(grp) == pc
+            assert [shard.grid_coords(r, world)[1] for r in grp] == list(range(pc))
+        # the chunks of all slices tile [0, l) exactly
+        l, sub = 128 * pr * 3 * 2, 3
+        ranges = sorted(shard.chunk_range(l, pr, sub, g, j) for g in range(pr) for j in range(sub))
+        assert ranges[0][0] == 0 and ranges[-1][1] == l and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    with pytest.raises(ValueError):
+        shard.chunk_range(1000, 2, 1, 0, 0)
+
+
+def _worker_pipe(rank, world, port, m, l, n, sub, accumulate, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pr, pc = shard.grid_shape(world)
+    gr, gc = shard.grid_coords(rank, world)
+    col_groups = [dist.new_group(shard.column_group(g, world)) for g in range(pc)]
+    row_groups = [dist.new_group(shard.row_group(g * pc, world)) for g in range(pr)]
+    rng = np.random.default_rng(44)
+    wl, wn = l // 64, n // 64
+    A = rng.integers(0, 2**64, size=(m, wl), dtype=np.uint64)
+    B = rng.integers(0, 2**64, size=(l, wn), dtype=np.uint64)
+    Cin = rng.integers(0, 2**64, size=(m, wn), dtype=np.uint64)
+    r0, r1 = shard.row_blocks(m, pr)[gr]
+    c0, c1 = shard.col_blocks(n, pc)[gc]
+    w0, w1 = c0 // 64, c1 // 64
+    rows, kc = r1 - r0, l // (pr * sub)
+    part_rows = rows // pc
+    assert rows % pc == 0 and rows % 2 == 0
+    devA = {}                                                           # (g, j) -> [rows, kc/64], filled part by part
+    devB = [np.zeros((pr, kc, w1 - w0), dtype=np.uint64) for _ in range(sub)]
+    devC = np.zeros((rows, w1 - w0), dtype=np.uint64)
+    hostC = np.full((rows, w1 - w0), 0xAAAAAAAAAAAAAAAA, dtype=np.uint64)
+    log = []
+
+    class Ops:
+        def upload_c(self):
+            devC[:, :] = Cin[r0:r1, w0:w1]
+
+        def upload_b(self, j):
+            k0, k1 = shard.chunk_range(l, pr, sub, gr, j)
+            devB[j][gr] = B[k0:k1, w0:w1]
+
+        def gather_b(self, j):
+            log.append(("b", j))
+            out = torch.empty((pr, kc, w1 - w0), dtype=torch.int64)
+            dist.all_gather_into_tensor(out.view(-1), torch.from_numpy(devB[j][gr].view(np.int64)).reshape(-1), group=col_groups[gc])
+            devB[j][:, :, :] = out.numpy().view(np.uint64)
+
+        def upload_a(self, g, j):
+            k0, k1 = shard.chunk_range(l, pr, sub, g, j)
+            buf = np.zeros((rows, kc // 64), dtype=np.uint64)
+            buf[gc * part_rows:(gc + 1) * part_rows] = A[r0 + gc * part_rows:r0 + (gc + 1) * part_rows, k0 // 64:k1 // 64]
+            devA[(g, j)] = buf
+
+        def gather_a(self, g, j):
+            log.append(("a", g, j))
+            buf = devA[(g, j)]
+            out = torch.empty(buf.shape, dtype=torch.int64)
+            mine = torch.from_numpy(buf[gc * part_rows:(gc + 1) * part_rows].view(np.int64)).reshape(-1)
+            dist.all_gather_into_tensor(out.view(-1), mine, group=row_groups[gr])
+            buf[:, :] = out.numpy().view(np.uint64)
+
+        def mul(self, g, j, clear, part):
+            i, nparts = part if part else (0, 1)
+            a0, a1 = i * rows // nparts, (i + 1) * rows // nparts
+            Am, Bm = _matrix_from(devA[(g, j)][a0:a1], kc), _matrix_from(devB[j][g], c1 - c0)
+            Cm = _matrix_from(np.zeros_like(devC[a0:a1]) if clear else devC[a0:a1], c1 - c0)
+            H.oracle().orc_addmul(Cm, Am, Bm, 0)
+            devC[a0:a1] = H.storage(Cm)[:, : w1 - w0]
+            H.free(Am, Bm, Cm)
+
+        def download(self, part):
+            i, nparts = part
+            a0, a1 = i * rows // nparts, (i + 1) * rows // nparts
+            hostC[a0:a1] = devC[a0:a1]
+
+    shard.pipelined_product(rank, world, Ops(), sub=sub, accumulate=accumulate)
+    gathered = [None] * world
+    dist.gather_object((r0, r1, w0, w1, hostC, log), gathered if rank == 0 else None, dst=0)
+    if rank == 0:
+        C = np.zeros((m, wn), dtype=np.uint64)
+        for g0, g1, v0, v1, blk, _ in gathered:
+            C[g0:g1, v0:v1] = blk
+        Am, Bm = _matrix_from(A, l), _matrix_from(B, n)
+        Cm = _matrix_from(Cin if accumulate else np.zeros_like(Cin), n)
+        H.oracle().orc_addmul(Cm, Am, Bm, 0)
+        ok = bool(np.array_equal(C, H.storage(Cm)[:, :wn]))
+        # collectives were issued in the same communicator order by every rank (the no-deadlock argument)
+        kinds = [[e[0] for e in lg] for *_, lg in gathered]
+        ok = ok and all(k == kinds[0] for k in kinds)
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,sub,accumulate", [(2, (128, 512, 256), 1, False), (2, (256, 1024, 128), 2, True),
+                                                        (4, (256, 512, 256), 1, False), (4, (128, 1024, 256), 2, True)])
+def test_pipelined_product_over_gloo(world, shape, sub, accumulate):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() + world * 13 + shape[1] + sub) % 2000
+    procs = [ctx.Process(target=_worker_pipe, args=(r, world, port, *shape, sub, accumulate, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True

@@ -81,20 +81,35 @@ def main():
                 c = ((n // 32) + 3) // 4 * 4
                 return torch.full((r * c,), 127, device=dev, dtype=torch.uint8).view(torch.float8_e8m0fnu)   # 2^0
             sa, sb = scales(n), scales(n)
-            for out_dtype in (torch.float32, torch.bfloat16):
-                try:
-                    fn = lambda: torch._scaled_mm(a4, b4.t(), scale_a=sa, scale_b=sb, out_dtype=out_dtype)  # noqa: E731
-                    ms = timeit(fn)
-                    c = fn()
-                    exact = None
-                    if ref_lsb is not None and out_dtype == torch.float32:
-                        exact = bool(torch.equal((c.to(torch.int64) & 1).to(torch.uint8), ref_lsb))
-                    print(json.dumps({"probe": "cublasLt mxfp4 e2m1 (torch._scaled_mm)", "out": str(out_dtype), "n": n, "ms": ms,
-                                      "bitops_per_s": ops / (ms * 1e-3), "lsb_exact_vs_int8": exact,
-                                      "max": float(c.max())}), flush=True)
-                    del c
-                except Exception as e:  # noqa: BLE001
-                    print(json.dumps({"probe": "fp4", "out": str(out_dtype), "n": n, "error": repr(e)[:300]}), flush=True)
+            import torch.nn.functional as F
+            from torch.nn.functional import ScalingType, SwizzleType
+            sa2, sb2 = sa.view(-1, n // 32), sb.view(-1, n // 32)
+            variants = {
+                "F.scaled_mm 1x32 swizzled flat": lambda od: F.scaled_mm(a4, b4.t(), sa, ScalingType.BlockWise1x32, sb, ScalingType.BlockWise1x32,
+                                                                         swizzle_a=SwizzleType.SWIZZLE_32_4_4, swizzle_b=SwizzleType.SWIZZLE_32_4_4, output_dtype=od),
+                "F.scaled_mm 1x32 swizzled 2d": lambda od: F.scaled_mm(a4, b4.t(), sa2, ScalingType.BlockWise1x32, sb2, ScalingType.BlockWise1x32,
+                                                                       swizzle_a=SwizzleType.SWIZZLE_32_4_4, swizzle_b=SwizzleType.SWIZZLE_32_4_4, output_dtype=od),
+                "_scaled_mm 2d scales": lambda od: torch._scaled_mm(a4, b4.t(), scale_a=sa2, scale_b=sb2, out_dtype=od),
+            }
+            done = set()
+            for vname, call in variants.items():
+                for out_dtype in (torch.float32, torch.bfloat16):
+                    if out_dtype in done:
+                        continue
+                    try:
+                        fn = lambda: call(out_dtype)  # noqa: E731
+                        ms = timeit(fn)
+                        c = fn()
+                        exact = None
+                        if ref_lsb is not None and out_dtype == torch.float32:
+                            exact = bool(torch.equal((c.to(torch.int64) & 1).to(torch.uint8), ref_lsb))
+                        print(json.dumps({"probe": "cublasLt mxfp4 e2m1 (" + vname + ")", "out": str(out_dtype), "n": n, "ms": ms,
+                                          "bitops_per_s": ops / (ms * 1e-3), "lsb_exact_vs_int8": exact,
+                                          "max": float(c.max())}), flush=True)
+                        done.add(out_dtype)
+                        del c
+                    except Exception as e:  # noqa: BLE001
+                        print(json.dumps({"probe": "fp4 " + vname, "out": str(out_dtype), "n": n, "error": repr(e)[:400]}), flush=True)
         except Exception as e:  # noqa: BLE001
             print(json.dumps({"probe": "fp4", "n": n, "error": repr(e)[:300]}), flush=True)
         # ---- the expansion the tensor path would need (bit-packed -> one byte per element), HBM-bound ----
