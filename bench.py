@@ -354,10 +354,122 @@ def run_own_arm(args):
         exchange()
         device_product()
 
+    # ---- N > 1, end to end: the K-chunk pipeline of m4ri_b200/shard.py (pipelined_product) on this rank's GPU -------
+    # uploads ride their own stream, exchanges and products the compute stream, downloads a third stream; every
+    # operand bit crosses PCIe once per node (row group: 1/pc of an A chunk's rows per rank, column group: 1/pr of B)
+    pipe = None
+    if world > 1 and not args.serial_e2e:
+        sub = args.ksub
+        kc = l // (pr * sub)
+        if l % (pr * sub * 128) or rows % (pc * 2 * 64):
+            raise SystemExit("--ksub: K-chunks must be multiples of 128 columns and the row block divisible by 128 * pc")
+        part_rows = rows // pc
+        row_grp = None
+        if pc > 1:      # every rank creates every row group, in the same order
+            rgroups = [dist.new_group(shard.row_group(g * pc, world, args.grid)) for g in range(pr)]
+            row_grp = rgroups[gr]
+        up_stream, dn_stream = torch.cuda.Stream(), torch.cuda.Stream()
+        uh, dh = ctypes.c_void_p(up_stream.cuda_stream), ctypes.c_void_p(dn_stream.cuda_stream)
+        kw = kc // 64
+        tAc = {(g, j): torch.zeros((rows, kw), dtype=torch.int64, device="cuda") for g in range(pr) for j in range(sub)}
+        tBc = [torch.zeros((pr, kc, pitchb), dtype=torch.int64, device="cuda") for _ in range(sub)]
+        tCe = torch.zeros((rows, pitchb), dtype=torch.int64, device="cuda")
+        TAIL = 2
+        wrap = lib.m4ri_b200_dmat_wrap
+
+        class Pipe:
+            def __init__(self):
+                self.dA = {k: wrap(t.data_ptr(), kw, rows, kc) for k, t in tAc.items()}
+                self.dApart = {k: wrap(t[gc * part_rows:].data_ptr(), kw, part_rows, kc) for k, t in tAc.items()}
+                self.dAtail = {(k, i): wrap(t[i * rows // TAIL:].data_ptr(), kw, rows // TAIL, kc) for k, t in tAc.items() for i in range(TAIL)}
+                self.dB = {(j, g): wrap(tBc[j][g].data_ptr(), pitchb, kc, ncb) for j in range(sub) for g in range(pr)}
+                self.dC = wrap(tCe.data_ptr(), pitchb, rows, ncb)
+                self.dCtail = [wrap(tCe[i * rows // TAIL:].data_ptr(), pitchb, rows // TAIL, ncb) for i in range(TAIL)]
+                self.ev = {}
+                self.tail_ev = [None] * TAIL
+
+            def bind(self, hs):    # host windows of this step's operands (headers only; same words)
+                self.hs = hs
+                WIN = 0x4
+                self.hA, self.hB, self.hC = {}, {}, []
+                for g in range(pr):
+                    for j in range(sub):
+                        k0, _ = shard.chunk_range(l, pr, sub, g, j)
+                        h = make_header(MzdT, hs.A[gc * part_rows:, k0 // 64:].ctypes.data, part_rows, kc, pitch)
+                        h.flags |= WIN
+                        self.hA[(g, j)] = h
+                for j in range(sub):
+                    h = make_header(MzdT, hs.B[j * kc:].ctypes.data, kc, ncb, pitchb)
+                    h.flags |= WIN
+                    self.hB[j] = h
+                for i in range(TAIL):
+                    h = make_header(MzdT, hs.C[i * rows // TAIL:].ctypes.data, rows // TAIL, ncb, pitchb)
+                    h.flags |= WIN
+                    self.hC.append(h)
+
+            def _mark(self, key):
+                e = torch.cuda.Event()
+                e.record(up_stream)
+                self.ev[key] = e
+
+            def upload_c(self):
+                lib.m4ri_b200_upload(self.dC, ctypes.byref(self.hs.mC), uh)
+                self._mark("c")
+
+            def upload_b(self, j):
+                lib.m4ri_b200_upload(self.dB[(j, gr)], ctypes.byref(self.hB[j]), uh)
+                self._mark(("b", j))
+
+            def gather_b(self, j):
+                tstream.wait_event(self.ev[("b", j)])
+                dist.all_gather_into_tensor(tBc[j].view(-1), tBc[j][gr].view(-1), group=group)
+
+            def upload_a(self, g, j):
+                lib.m4ri_b200_upload(self.dApart[(g, j)], ctypes.byref(self.hA[(g, j)]), uh)
+                self._mark(("a", g, j))
+
+            def gather_a(self, g, j):
+                tstream.wait_event(self.ev[("a", g, j)])
+                t = tAc[(g, j)]
+                dist.all_gather_into_tensor(t.view(-1), t[gc * part_rows:(gc + 1) * part_rows].view(-1), group=row_grp)
+
+            def mul(self, g, j, clear, part):
+                tstream.wait_event(self.ev[("a", g, j)])
+                if g == gr:
+                    tstream.wait_event(self.ev[("b", j)])
+                if "c" in self.ev:
+                    tstream.wait_event(self.ev["c"])
+                dCp, dAp = (self.dC, self.dA[(g, j)]) if part is None else (self.dCtail[part[0]], self.dAtail[((g, j), part[0])])
+                if args.chunk_levels >= 0:
+                    lib.m4ri_b200_dmul_levels(dCp, dAp, self.dB[(j, g)], args.chunk_levels, 1 if clear else 0, sh)
+                elif leaf_only:
+                    lib.m4ri_b200_dmul_m4rm(dCp, dAp, self.dB[(j, g)], 1 if clear else 0, sh)
+                else:
+                    lib.m4ri_b200_dmul(dCp, dAp, self.dB[(j, g)], cutoff, 1 if clear else 0, sh)
+                if part is not None:
+                    e = torch.cuda.Event()
+                    e.record(tstream)
+                    self.tail_ev[part[0]] = e
+
+            def download(self, part):
+                dn_stream.wait_event(self.tail_ev[part[0]])
+                lib.m4ri_b200_download(ctypes.byref(self.hC[part[0]]), self.dCtail[part[0]], dh)   # returns when the part is on the host
+
+            def step(self, hs):
+                if getattr(self, "hs", None) is not hs:
+                    self.bind(hs)
+                self.ev = {}
+                up_stream.wait_stream(tstream)     # buffers of the previous step are free again
+                shard.pipelined_product(rank, world, self, sub=sub, mode=args.grid, tail_parts=TAIL, accumulate=accumulate)
+
+        pipe = Pipe()
+
     def step_e2e(hs):
         if world == 1:   # the drop-in call itself
             getattr(lib, fn_name)(ctypes.byref(hs.mC), ctypes.byref(hs.mA), ctypes.byref(hs.mB), cutoff)
-        else:
+        elif pipe is not None:
+            pipe.step(hs)
+        else:            # --serial-e2e: upload, exchange, multiply, download one after the other (round-1 form)
             lib.m4ri_b200_upload(dA, ctypes.byref(hs.mA), sh)
             lib.m4ri_b200_upload(dBs, ctypes.byref(hs.mB), sh)
             if accumulate:
@@ -446,7 +558,9 @@ def run_own_arm(args):
         e2e[k] = {"value": total_bitops / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": d2h, "host_memory": k,
                   "api": f"{fn_name}(C, A, B, cutoff) on host mzd_t" if world == 1 else
-                  "upload + all_gather + m4ri_b200_dmul + download per rank"}
+                  ("upload + all_gather + m4ri_b200_dmul + download per rank, one after the other" if pipe is None else
+                   f"K-chunk pipeline per rank ({pr * args.ksub} chunks of {l // (pr * args.ksub)} columns: uploads, NVLink "
+                   f"all-gathers in row/column groups, products and downloads overlapped; m4ri_b200/shard.py)")}
 
     # ---- verification (after the timed legs; default on) -------------------------------------------------
     verified = None
@@ -665,6 +779,9 @@ def main():
     ap.add_argument("--pinned", action="store_true", help="only the pinned end-to-end leg")
     ap.add_argument("--grid", default="auto", choices=["auto", "rows"],
                     help="C partition over ranks: 'rows' = row-blocks only; 'auto' = two column blocks from 4 ranks on")
+    ap.add_argument("--serial-e2e", action="store_true", help="N > 1: end-to-end leg without the K-chunk pipeline")
+    ap.add_argument("--ksub", type=int, default=1, help="N > 1 end to end: sub-chunks per B row-slice (K-chunks = pr * ksub)")
+    ap.add_argument("--chunk-levels", type=int, default=-1, help="N > 1 end to end: Strassen levels of a chunk product (-1: library rule)")
     ap.add_argument("--no-check", action="store_true", help="skip the verification after the timed legs")
     ap.add_argument("--verify", action="store_true", help="check this rank's C block against the oracle (small --size only)")
     args = ap.parse_args()
