@@ -49,12 +49,13 @@ typedef struct mzd_t {
 #endif
 
 /* C = A*B, Strassen-Winograd above the M4RM leaf.  C may be NULL (allocated, caller
- * frees with mzd_free).  cutoff 0 = library default, <0 dies.  m4ri/strassen.h:68,
+ * frees with mzd_free).  cutoff 0 = library default, <0 dies.  m4ri/strassen.h:52,
  * strassen.c:345-365. */
 mzd_t *mzd_mul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
-/* C ^= A*B.  m4ri/strassen.h:88, strassen.c:675-700. */
+/* C ^= A*B.  m4ri/strassen.h:68, strassen.c:675-700. */
 mzd_t *mzd_addmul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
-/* unchecked variants.  m4ri/strassen.h:52,109,126; strassen.c:41,367,667. */
+/* unchecked variants.  m4ri/strassen.h:88 (_mzd_mul_even), :109 (_mzd_addmul_even), :126 (_mzd_addmul);
+ * strassen.c:41,367,667. */
 mzd_t *_mzd_mul_even(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
 mzd_t *_mzd_addmul_even(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
 mzd_t *_mzd_addmul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
@@ -65,10 +66,14 @@ mzd_t *mzd_mul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k);
 mzd_t *mzd_addmul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k);
 mzd_t *_mzd_mul_m4rm(mzd_t *C, mzd_t const *A, mzd_t const *B, int k, int clear);
 /* block-parallel multiply: the reference splits C 2x2 over four OpenMP sections
- * (m4ri/mp.h:47,62; mp.c:277-324); here C's row-blocks are split over the visible
- * GPUs (m4ri_b200_set_num_devices). */
+ * (m4ri/mp.h:47,62; mp.c:277-324); here C is cut into pr x pc blocks over the GPUs chosen with
+ * m4ri_b200_set_num_devices (2 column blocks from four GPUs on — the reference's 2 x 2 shape, mp.c:179-228),
+ * operands cross PCIe once per box and are exchanged over NVLink, transfers overlap the products. */
 mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
 mzd_t *mzd_addmul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
+/* the unchecked block forms behind them (m4ri/mp.h:74,86; mp.c:39-156, 158-275) */
+mzd_t *_mzd_mul_mp4(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
+mzd_t *_mzd_addmul_mp4(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
 
 /* Widened rows (callers of the multiplication path): triangular solves with matrices, X overwrites B,
  * unit diagonal implied, only the strict triangle of the triangular operand is read.
@@ -111,6 +116,9 @@ uint64_t m4ri_b200_profile_end(double *leaf_ms, double *leaf_bitops);
 mzd_t *m4ri_b200_mzd_init(rci_t r, rci_t c);
 mzd_t *m4ri_b200_mzd_init_window(mzd_t *M, rci_t lowr, rci_t lowc, rci_t highr, rci_t highc);
 void   m4ri_b200_mzd_free(mzd_t *M);
+/* frees a result this library allocated for a NULL C / DST argument (it comes from the process' libm4ri
+ * mzd_init when one is loaded, else from m4ri_b200_mzd_init) */
+void   m4ri_b200_result_free(mzd_t *M);
 
 /* Device-resident matrix: bit-packed rows exactly like mzd_t (64-bit words, LSB-first),
  * pitch a multiple of 2 words, base 16-byte aligned, and every bit between ncols and

@@ -457,25 +457,58 @@ M4B_TRSM_ENTRY(trsm_lower_right, false, false)
 M4B_TRSM_ENTRY(trsm_upper_right, true, false)
 #undef M4B_TRSM_ENTRY
 
-// Row-blocks of C over the GPUs chosen with m4ri_b200_set_num_devices (multi.cu); one GPU: same as mzd_mul.
+// C blocks over the GPUs chosen with m4ri_b200_set_num_devices (multi.cu), starting at the selected device; with one
+// usable GPU: same as mzd_mul / mzd_addmul.
+static int mp_devices() {
+  Ctx &c = ctx();
+  int avail = 0;
+  M4B_CUDA(cudaGetDeviceCount(&avail));
+  int const G = c.num_devices < avail - c.device ? c.num_devices : avail - c.device;
+  return G < 1 ? 1 : G;
+}
+
 mzd_t *mzd_mul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
   M4B_LOCKED;
-  if (ctx().num_devices <= 1) return mzd_mul(C, A, B, cutoff);
+  int const G = mp_devices();
+  if (G <= 1) return mzd_mul(C, A, B, cutoff);
   if (A->ncols != B->nrows) die("mzd_mul_mp: A ncols (%d) need to match B nrows (%d).\n", A->ncols, B->nrows);
   cutoff = norm_cutoff(cutoff, "mzd_mul_mp");
   C = checked("mzd_mul_mp", C, A, B);
-  multi_product(C, A, B, cutoff, true, ctx().num_devices, ctx().last_path, sizeof ctx().last_path);
+  ++g_products;
+  multi_product(C, A, B, cutoff, true, G, ctx().device, ctx().last_path, sizeof ctx().last_path);
   return C;
 }
 
 mzd_t *mzd_addmul_mp(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
   M4B_LOCKED;
-  if (ctx().num_devices <= 1) return mzd_addmul(C, A, B, cutoff);
+  int const G = mp_devices();
+  if (G <= 1) return mzd_addmul(C, A, B, cutoff);
   if (A->ncols != B->nrows) die("mzd_addmul_mp: A ncols (%d) need to match B nrows (%d).\n", A->ncols, B->nrows);
   cutoff = norm_cutoff(cutoff, "mzd_addmul_mp");
   C = checked("mzd_addmul_mp", C, A, B);
   if (A->nrows == 0 || A->ncols == 0 || B->ncols == 0) return C;
-  multi_product(C, A, B, cutoff, false, ctx().num_devices, ctx().last_path, sizeof ctx().last_path);
+  ++g_products;
+  multi_product(C, A, B, cutoff, false, G, ctx().device, ctx().last_path, sizeof ctx().last_path);
+  return C;
+}
+
+// The reference's unchecked 2 x 2 block forms (m4ri/mp.h:74,86; mp.c:39-156, 158-275).  An OpenMP libm4ri would run
+// four concurrent _mzd_(add)mul_even sections here; interposed, the whole product goes to the GPU(s) at once.
+mzd_t *_mzd_mul_mp4(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  M4B_LOCKED;
+  int const G = mp_devices();
+  if (G <= 1) return _mzd_mul_even(C, A, B, cutoff);
+  ++g_products;
+  multi_product(C, A, B, cutoff < 64 ? 64 : cutoff, true, G, ctx().device, ctx().last_path, sizeof ctx().last_path);
+  return C;
+}
+
+mzd_t *_mzd_addmul_mp4(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
+  M4B_LOCKED;
+  int const G = mp_devices();
+  if (G <= 1) return _mzd_addmul_even(C, A, B, cutoff);
+  ++g_products;
+  multi_product(C, A, B, cutoff < 64 ? 64 : cutoff, false, G, ctx().device, ctx().last_path, sizeof ctx().last_path);
   return C;
 }
 
@@ -556,6 +589,15 @@ mzd_t *m4ri_b200_mzd_init_window(mzd_t *P, rci_t lowr, rci_t lowc, rci_t highr, 
   W->rowstride = P->rowstride;
   W->data = P->data + (int64_t)lowr * P->rowstride + lowc / 64;
   return W;
+}
+
+// Frees a matrix that an entry point of this library allocated for a NULL result argument: it came from the
+// process' libm4ri mzd_init when one is loaded (alloc_result), so it goes back through that library's mzd_free.
+void m4ri_b200_result_free(mzd_t *M) {
+  typedef void (*mzd_free_fn)(mzd_t *);
+  static mzd_free_fn ref_free = dlsym(RTLD_DEFAULT, "mzd_init") ? reinterpret_cast<mzd_free_fn>(dlsym(RTLD_DEFAULT, "mzd_free")) : nullptr;
+  if (ref_free) ref_free(M);
+  else m4ri_b200_mzd_free(M);
 }
 
 void m4ri_b200_mzd_free(mzd_t *M) {

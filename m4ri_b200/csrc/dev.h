@@ -42,8 +42,10 @@ extern unsigned long long g_kernel_launches;  // counted by every launcher in th
 // ---- leaf: C ^= A*B (M4RM, stream-K persistent kernel) -------------------------------
 // C must already hold the addend (zeros for a plain product).
 void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream);
-// up to 7 products of identical shape in ONE persistent launch (the last Strassen level)
+// products of identical shape in ONE persistent launch: 7 (the last Strassen level) with either leaf, up to 49
+// (the last TWO levels) where the tall-tile leaf suits — m4rm_batch_limit() says which
 void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream);
+int  m4rm_batch_limit(int m, int l, int n);
 // C = A*B for l <= 128 with plain stores; C may alias A or B
 void launch_m4rm_overwrite(DView C, DView A, DView B, cudaStream_t stream);
 int  m4rm_num_sms();
@@ -67,6 +69,10 @@ void launch_transpose(DView dst, DView src, cudaStream_t stream);        // dst 
 void launch_winograd_pre_a(DView const a[4], DView const s_out[4], cudaStream_t stream);
 void launch_winograd_pre_b(DView const b[4], DView const t_out[4], cudaStream_t stream);
 void launch_winograd_post(DView const p[7], DView const c[4], bool accumulate, cudaStream_t stream);
+// the same for up to 7 nodes of identical shape in one launch (arrays indexed [node * 4 + q] / [node * 7 + i])
+void launch_winograd_pre_a_batch(int nodes, DView const *a, DView const *s_out, cudaStream_t stream);
+void launch_winograd_pre_b_batch(int nodes, DView const *b, DView const *t_out, cudaStream_t stream);
+void launch_winograd_post_batch(int nodes, DView const *p, DView const *c, cudaStream_t stream);
 
 // ---- host <-> device transfers (capi.cu) ----------------------------------------------
 class Stager;   // staging.h: pinned-ring transfers for pageable host memory (optional)
@@ -75,8 +81,10 @@ void download(mzd_t *dst, DView src, cudaStream_t s, std::vector<word> &tmp, Sta
 void zero_async(DView v, cudaStream_t s);
 
 // ---- multi-GPU row-block product (multi.cu) --------------------------------------------
-void multi_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool clear, int num_devices,
+// GPUs base_device .. base_device + num_devices - 1; C cut into pr x pc blocks (multi_grid)
+void multi_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool clear, int num_devices, int base_device,
                    char *path_out, size_t path_len);
+void multi_grid(int num_devices, int ncols, int *pr, int *pc);
 void multi_release();
 
 // ---- host scheduler ------------------------------------------------------------------

@@ -4,6 +4,8 @@
 //
 // All views handed to these kernels are 16-byte aligned and 128-bit padded (dev.h), so every
 // access is a coalesced 128-bit load/store; grid = a multiple of the SM count, grid-stride loop.
+#include <string.h>
+
 #include "dev.h"
 
 namespace m4b {
@@ -69,8 +71,14 @@ __device__ __forceinline__ uint4 x4(uint4 a, uint4 const &b) { a.x ^= b.x; a.y ^
 // MODE 0: in = A11 A12 A21 A22 -> out = S1 S2 S3 S4      (S1 = A21+A22, S2 = S1+A11, S3 = A11+A21, S4 = A12+S2)
 // MODE 1: in = B11 B12 B21 B22 -> out = T1 T2 T3 T4      (T1 = B12+B11, T2 = B22+T1, T3 = B22+B12, T4 = T2+B21)
 // MODE 2: in = P1..P7 -> out = C11 C12 C21 C22 (overwrite)   MODE 3: same, accumulated onto C
+constexpr int kMaxNodes = 7;     // nodes of identical shape handled by one launch (blockIdx.y)
+struct VBatch {
+  VSet in[kMaxNodes], out[kMaxNodes];
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(256) winograd_ew_kernel(VSet in, VSet out, int rows, int w128) {
+__global__ void __launch_bounds__(256) winograd_ew_kernel(const __grid_constant__ VBatch batch, int rows, int w128) {
+  VSet const &in = batch.in[blockIdx.y], &out = batch.out[blockIdx.y];
   int64_t const total = (int64_t)rows * w128;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t const r = i / w128;
@@ -100,18 +108,23 @@ __global__ void __launch_bounds__(256) winograd_ew_kernel(VSet in, VSet out, int
   }
 }
 
+// `nodes` Winograd nodes of identical shape in one launch: in[node * nin + k], out[node * nout + k]
 template <int MODE>
-void launch_winograd_ew(DView const *in, int nin, DView const *out, int nout, cudaStream_t s) {
+void launch_winograd_ew(DView const *in, int nin, DView const *out, int nout, cudaStream_t s, int nodes = 1) {
   int const rows = out[0].nrows, w128 = (out[0].ncols + 127) / 128;
   if (rows <= 0 || w128 <= 0) return;
-  VSet vi, vo;
-  for (int k = 0; k < nin; ++k) vi.v[k] = v128(in[k]);
-  for (int k = 0; k < nout; ++k) vo.v[k] = v128(out[k]);
+  if (nodes > kMaxNodes) die("m4ri_b200: %d Winograd nodes in one launch exceed %d\n", nodes, kMaxNodes);
+  VBatch b;
+  memset(&b, 0, sizeof b);
+  for (int nd = 0; nd < nodes; ++nd) {
+    for (int k = 0; k < nin; ++k) b.in[nd].v[k] = v128(in[nd * nin + k]);
+    for (int k = 0; k < nout; ++k) b.out[nd].v[k] = v128(out[nd * nout + k]);
+  }
   int64_t const total = (int64_t)rows * w128;
   int64_t blocks = (total + 255) / 256;
-  int64_t const cap = (int64_t)m4rm_num_sms() * 8;
+  int64_t const cap = ((int64_t)m4rm_num_sms() * 8 + nodes - 1) / nodes;
   if (blocks > cap) blocks = cap;
-  winograd_ew_kernel<MODE><<<(unsigned)blocks, 256, 0, s>>>(vi, vo, rows, w128);
+  winograd_ew_kernel<MODE><<<dim3((unsigned)blocks, (unsigned)nodes), 256, 0, s>>>(b, rows, w128);
   M4B_CUDA(cudaGetLastError());
   ++g_kernel_launches;
 }
@@ -137,6 +150,11 @@ void launch_winograd_post(DView const p[7], DView const c[4], bool accumulate, c
   if (accumulate) launch_winograd_ew<3>(p, 7, c, 4, s);
   else            launch_winograd_ew<2>(p, 7, c, 4, s);
 }
+
+// the same for `nodes` (<= 7) nodes of identical shape: a[node * 4 + q] etc.
+void launch_winograd_pre_a_batch(int nodes, DView const *a, DView const *s_out, cudaStream_t s) { launch_winograd_ew<0>(a, 4, s_out, 4, s, nodes); }
+void launch_winograd_pre_b_batch(int nodes, DView const *b, DView const *t_out, cudaStream_t s) { launch_winograd_ew<1>(b, 4, t_out, 4, s, nodes); }
+void launch_winograd_post_batch(int nodes, DView const *p, DView const *c, cudaStream_t s) { launch_winograd_ew<2>(p, 7, c, 4, s, nodes); }
 
 void launch_xor(DView C, DView A, DView B, cudaStream_t s) { launch_ew<0>(C, A, B, s); }
 void launch_copy(DView C, DView A, cudaStream_t s) { launch_ew<1>(C, A, A, s); }

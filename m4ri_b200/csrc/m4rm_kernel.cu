@@ -470,9 +470,17 @@ static int leaf_variant() {
   return g_leaf_variant;
 }
 
+static bool tall_leaf(int m, int l, int n, bool overwrite) {
+  int const variant = leaf_variant();
+  return !overwrite && (variant == 2 || (variant == 0 && leaf2_suits(m, l, n)));
+}
+
+int m4rm_batch_limit(int m, int l, int n) { return tall_leaf(m, l, n, false) ? 49 : kMaxBatch; }
+
 static void launch_leaf(int count, DView const *C, DView const *A, DView const *B, bool overwrite, cudaStream_t stream) {
   if (count <= 0 || A[0].nrows <= 0 || A[0].ncols <= 0 || B[0].ncols <= 0) return;   // empty product: C unchanged
-  if (count > kMaxBatch) die("m4ri_b200: batch of %d leaf products exceeds %d\n", count, kMaxBatch);
+  if (count > m4rm_batch_limit(A[0].nrows, A[0].ncols, B[0].ncols))
+    die("m4ri_b200: batch of %d leaf products exceeds the limit of this leaf\n", count);
   std::pair<cudaEvent_t, cudaEvent_t> *ev = nullptr;
   if (g_prof.on) {
     if (g_prof.used == g_prof.pool.size()) {
@@ -485,8 +493,7 @@ static void launch_leaf(int count, DView const *C, DView const *A, DView const *
     g_prof.bitops += 2.0 * count * A[0].nrows * (double)A[0].ncols * B[0].ncols;
     M4B_CUDA(cudaEventRecord(ev->first, stream));
   }
-  int const variant = leaf_variant();
-  bool const tall = !overwrite && (variant == 2 || (variant == 0 && leaf2_suits(A[0].nrows, A[0].ncols, B[0].ncols)));
+  bool const tall = tall_leaf(A[0].nrows, A[0].ncols, B[0].ncols, overwrite);
   g_last_leaf = tall ? 2 : 1;
   if (tall)
     launch_m4rm_leaf2(count, C, A, B, stream);                       // tall tiles: 4096 rows x 256 bits

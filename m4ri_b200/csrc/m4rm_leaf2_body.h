@@ -53,7 +53,7 @@ constexpr int kOffBar       = kOffB + 2 * kBSlabBytes;
 constexpr int kOffSeg       = kOffBar + 16;               // {prob, tn, row0, s0} of the current segment
 constexpr int kSmemBytes    = kOffBar + 64;               // 204 864 B  (limit 232 448)
 constexpr uint32_t kSlabTxBytes = kASlabBytes;
-constexpr int kMaxBatch     = 7;
+constexpr int kMaxBatch     = 49;                        // two Strassen levels in one launch (7.9 KB of kernel parameters)
 
 struct alignas(64) Args {
   TMap mapA[kMaxBatch];          // a3d: 3D (words, 256 rows, row groups), box 4 x 256 x 16 = one slab of a tile;

@@ -52,7 +52,9 @@ size_t strassen_workspace_bytes(int m, int k, int n, int levels) {
   size_t total = 0;
   for (int lv = 0; lv < levels; ++lv) {
     m /= 2; k /= 2; n /= 2;
-    total += 4 * Workspace::bytes_for(m, k) + 4 * Workspace::bytes_for(k, n) + Workspace::bytes_for(7 * m, n);
+    // the last level of a two-level node (winograd_node2) holds the temporaries of all seven children at once
+    size_t const live = (levels >= 2 && lv == levels - 1) ? 7 : 1;
+    total += live * (4 * Workspace::bytes_for(m, k) + 4 * Workspace::bytes_for(k, n) + Workspace::bytes_for(7 * m, n));
   }
   return total;
 }
@@ -71,10 +73,16 @@ static void quadrants(DView const &V, DView q[4]) {
 //   post  C11 C12 C21 C22 from P1..P7                          (1 fused element-wise launch)
 // Same products as strassen.c's sequence (Winograd's 7-product form), different bookkeeping: more
 // temporaries (HBM is 180 GB), a third of the element-wise traffic and 3-4 launches instead of 29.
+static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws, cudaStream_t s);
+
 static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s) {
   if (levels == 0) {
     if (clear) launch_zero(C, s);
     launch_m4rm(C, A, B, s);
+    return;
+  }
+  if (levels == 2 && m4rm_batch_limit(A.nrows / 4, A.ncols / 4, B.ncols / 4) >= 49 && !getenv("M4RI_B200_NO_NODE2")) {
+    winograd_node2(C, A, B, clear, ws, s);
     return;
   }
   DView a[4], b[4], c[4];
@@ -100,6 +108,57 @@ static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Wor
     for (int i = 0; i < 7; ++i) winograd_node(P[i], X[i], Y[i], levels - 1, true, ws, s);
   }
   launch_winograd_post(P, c, !clear, s);
+  ws.release(mark);
+}
+
+// The last TWO levels as one node: 49 leaf products in ONE persistent launch and the additions of the seven
+// inner nodes batched into single launches.  A leaf launch costs ~35 us of fill and drain whatever its size
+// (every CTA of the stream-K partition ends with its red.xor merge at the same moment), which is 12 % of a
+// 7 x 4096^3 launch but 2 % of a 49 x 4096^3 one — this is what makes one more Strassen level pay.
+static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws, cudaStream_t s) {
+  DView a[4], b[4], c[4];
+  quadrants(A, a);
+  quadrants(B, b);
+  quadrants(C, c);
+  int const m2 = a[0].nrows, k2 = a[0].ncols, n2 = b[0].ncols, m4 = m2 / 2, k4 = k2 / 2, n4 = n2 / 2;
+  size_t const mark = ws.mark();
+  // ---- level 1 operands ----
+  DView S[4], T[4], P1[7];
+  for (int i = 0; i < 4; ++i) S[i] = ws.alloc(m2, k2);
+  for (int i = 0; i < 4; ++i) T[i] = ws.alloc(k2, n2);
+  DView const P1all = ws.alloc(7 * m2, n2);
+  for (int i = 0; i < 7; ++i) P1[i] = P1all.sub(i * m2, 0, (i + 1) * m2, n2);
+  launch_winograd_pre_a(a, S, s);
+  launch_winograd_pre_b(b, T, s);
+  DView const X1[7] = {a[0], a[1], S[3], a[3], S[0], S[1], S[2]};
+  DView const Y1[7] = {b[0], b[2], b[3], T[3], T[0], T[1], T[2]};
+  // ---- level 2 operands of all seven inner nodes ----
+  DView xa[28], xs[28], yb[28], yt[28], pq[28];
+  for (int i = 0; i < 7; ++i) {
+    quadrants(X1[i], xa + 4 * i);
+    quadrants(Y1[i], yb + 4 * i);
+    quadrants(P1[i], pq + 4 * i);
+    for (int q = 0; q < 4; ++q) xs[4 * i + q] = ws.alloc(m4, k4);
+    for (int q = 0; q < 4; ++q) yt[4 * i + q] = ws.alloc(k4, n4);
+  }
+  launch_winograd_pre_a_batch(7, xa, xs, s);
+  launch_winograd_pre_b_batch(7, yb, yt, s);
+  DView const P2all = ws.alloc(49 * m4, n4);
+  DView P2[49], X2[49], Y2[49];
+  for (int i = 0; i < 7; ++i) {
+    DView const *qa = xa + 4 * i, *qs = xs + 4 * i, *qb = yb + 4 * i, *qt = yt + 4 * i;
+    DView const X[7] = {qa[0], qa[1], qs[3], qa[3], qs[0], qs[1], qs[2]};
+    DView const Y[7] = {qb[0], qb[2], qb[3], qt[3], qt[0], qt[1], qt[2]};
+    for (int j = 0; j < 7; ++j) {
+      X2[7 * i + j] = X[j];
+      Y2[7 * i + j] = Y[j];
+      P2[7 * i + j] = P2all.sub((7 * i + j) * m4, 0, (7 * i + j + 1) * m4, n4);
+    }
+  }
+  launch_zero(P2all, s);
+  launch_m4rm_batch(49, P2, X2, Y2, s);
+  launch_winograd_post_batch(7, P2, pq, s);          // P1[i] from its seven products, all i in one launch
+  launch_winograd_post(P1, c, !clear, s);
   ws.release(mark);
 }
 
