@@ -358,7 +358,7 @@ def run_own_arm(args):
     # uploads ride their own stream, exchanges and products the compute stream, downloads a third stream; every
     # operand bit crosses PCIe once per node (row group: 1/pc of an A chunk's rows per rank, column group: 1/pr of B)
     pipe = None
-    if world > 1 and not args.serial_e2e:
+    if world > 1 and args.e2e_mode == "kchunk":
         sub = args.ksub
         kc = l // (pr * sub)
         if l % (pr * sub * 128) or rows % (pc * 2 * 64):
@@ -464,12 +464,133 @@ def run_own_arm(args):
 
         pipe = Pipe()
 
+    # ---- N > 1, end to end, default: the top Strassen level on separate quadrant buffers with transfer hooks ----------
+    # (m4ri_b200_dmul_quads): a rank uploads its 1/pc row share of an A quadrant and its 1/pr row share of a B quadrant
+    # when the schedule first needs them, the shares are all-gathered over NVLink inside the row / column group, and a
+    # C quadrant is downloaded as soon as it is final — the multi-rank form of the library's own host path
+    quads = None
+    if world > 1 and args.e2e_mode == "hooks" and not leaf_only:
+        from m4ri_b200 import DMatP, Hooks, HookFn
+        m2, k2, n2 = rows // 2, l // 2, ncb // 2
+        if rows % (2 * pc * 64) or l % (2 * pr * 128) or ncb % 256:
+            raise SystemExit("hooks mode: block dimensions must split into quadrants and per-rank shares")
+        if pc > 1:
+            rgroups2 = [dist.new_group(shard.row_group(g * pc, world, args.grid)) for g in range(pr)]
+            row_grp2 = rgroups2[gr]
+        up2, dn2 = torch.cuda.Stream(), torch.cuda.Stream()
+        uh2, dh2 = ctypes.c_void_p(up2.cuda_stream), ctypes.c_void_p(dn2.cuda_stream)
+        qa = [torch.zeros((m2, k2 // 64), dtype=torch.int64, device="cuda") for _ in range(4)]
+        qb = [torch.zeros((k2, n2 // 64), dtype=torch.int64, device="cuda") for _ in range(4)]
+        qc = [torch.zeros((m2, n2 // 64), dtype=torch.int64, device="cuda") for _ in range(4)]
+        wrap2 = lib.m4ri_b200_dmat_wrap
+        share_a, share_b = m2 // pc, k2 // pr           # rows of a quadrant this rank uploads
+        # this rank's share of B[:, cols gc] for this mode: the gr-th 1/pr of the rows of EACH row half (the resident and
+        # serial paths use one contiguous row-slice instead; still 1/world of B per rank)
+        srcB2 = [np.ascontiguousarray(H.seeded_words(H.SEED_B, share_b, n // 64, row0=h * k2 + gr * share_b)[:, wc0:wc1]) for h in range(2)]
+
+        class Quads:
+            def __init__(self):
+                self.dA = (DMatP * 4)(*[wrap2(t.data_ptr(), k2 // 64, m2, k2) for t in qa])
+                self.dB = (DMatP * 4)(*[wrap2(t.data_ptr(), n2 // 64, k2, n2) for t in qb])
+                self.dC = (DMatP * 4)(*[wrap2(t.data_ptr(), n2 // 64, m2, n2) for t in qc])
+                self.dAshare = [wrap2(t[gc * share_a:].data_ptr(), k2 // 64, share_a, k2) for t in qa]
+                self.dBshare = [wrap2(t[gr * share_b:].data_ptr(), n2 // 64, share_b, n2) for t in qb]
+                self.hooks = Hooks(HookFn(self.need_a), HookFn(self.need_b), HookFn(self.need_c), HookFn(self.done_c), None)
+                self.hostB = {}
+                self.error = None
+
+            def bind(self, hs):
+                self.hs = hs
+                if id(hs) not in self.hostB:      # B share of this mode, in the same kind of memory as the other operands
+                    if hs.pinned:
+                        tb = torch.empty((2, share_b, pitchb), dtype=torch.int64, pin_memory=True)
+                        arr = tb.numpy().view(np.uint64)
+                        self.hostB[id(hs)] = (arr, tb)
+                    else:
+                        arr = np.empty((2, share_b, pitchb), dtype=np.uint64)
+                        self.hostB[id(hs)] = (arr, None)
+                    arr[0], arr[1] = srcB2[0], srcB2[1]
+                hb = self.hostB[id(hs)][0]
+                WIN = 0x4
+                self.hA, self.hB, self.hC = [], [], []
+                for q in range(4):
+                    qr, qcol = q >> 1, q & 1
+                    h = make_header(MzdT, hs.A[qr * m2 + gc * share_a:, qcol * (k2 // 64):].ctypes.data, share_a, k2, pitch)
+                    h.flags |= WIN
+                    self.hA.append(h)
+                    h = make_header(MzdT, hb[qr][:, qcol * (n2 // 64):].ctypes.data, share_b, n2, pitchb)
+                    h.flags |= WIN
+                    self.hB.append(h)
+                    h = make_header(MzdT, hs.C[qr * m2:, qcol * (n2 // 64):].ctypes.data, m2, n2, pitchb)
+                    h.flags |= WIN
+                    self.hC.append(h)
+
+            def _guard(self, fn, q):
+                try:
+                    fn(q)
+                except BaseException as e:   # noqa: BLE001 — an exception must not unwind through the C++ frames
+                    self.error = e
+
+            def need_a(self, _user, q):
+                self._guard(self._need_a, q)
+
+            def need_b(self, _user, q):
+                self._guard(self._need_b, q)
+
+            def need_c(self, _user, q):
+                self._guard(self._need_c, q)
+
+            def done_c(self, _user, q):
+                self._guard(self._done_c, q)
+
+            def _uploaded(self):
+                e = torch.cuda.Event()
+                e.record(up2)
+                tstream.wait_event(e)
+
+            def _need_a(self, q):
+                lib.m4ri_b200_upload(self.dAshare[q], ctypes.byref(self.hA[q]), uh2)
+                self._uploaded()
+                if pc > 1:
+                    dist.all_gather_into_tensor(qa[q].view(-1), qa[q][gc * share_a:(gc + 1) * share_a].view(-1), group=row_grp2)
+
+            def _need_b(self, q):
+                lib.m4ri_b200_upload(self.dBshare[q], ctypes.byref(self.hB[q]), uh2)
+                self._uploaded()
+                if pr > 1:
+                    dist.all_gather_into_tensor(qb[q].view(-1), qb[q][gr * share_b:(gr + 1) * share_b].view(-1), group=group)
+
+            def _need_c(self, q):
+                lib.m4ri_b200_upload(self.dC[q], ctypes.byref(self.hC[q]), uh2)
+                self._uploaded()
+
+            def _done_c(self, q):
+                e = torch.cuda.Event()
+                e.record(tstream)
+                self.order.append((q, e))
+
+            def step(self, hs):
+                if getattr(self, "hs", None) is not hs:
+                    self.bind(hs)
+                self.order = []
+                up2.wait_stream(tstream)          # the quadrant buffers of the previous step are free again
+                lib.m4ri_b200_dmul_quads(self.dC, self.dA, self.dB, cutoff, 0 if accumulate else 1, sh, ctypes.byref(self.hooks))
+                if self.error is not None:
+                    raise self.error
+                for q, e in self.order:           # issued after the whole schedule: a download blocks this thread
+                    dn2.wait_event(e)
+                    lib.m4ri_b200_download(ctypes.byref(self.hC[q]), self.dC[q], dh2)
+
+        quads = Quads()
+
     def step_e2e(hs):
         if world == 1:   # the drop-in call itself
             getattr(lib, fn_name)(ctypes.byref(hs.mC), ctypes.byref(hs.mA), ctypes.byref(hs.mB), cutoff)
+        elif quads is not None:
+            quads.step(hs)
         elif pipe is not None:
             pipe.step(hs)
-        else:            # --serial-e2e: upload, exchange, multiply, download one after the other (round-1 form)
+        else:            # serial: upload, exchange, multiply, download one after the other (round-1 form)
             lib.m4ri_b200_upload(dA, ctypes.byref(hs.mA), sh)
             lib.m4ri_b200_upload(dBs, ctypes.byref(hs.mB), sh)
             if accumulate:
@@ -558,7 +679,9 @@ def run_own_arm(args):
         e2e[k] = {"value": total_bitops / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": d2h, "host_memory": k,
                   "api": f"{fn_name}(C, A, B, cutoff) on host mzd_t" if world == 1 else
-                  ("upload + all_gather + m4ri_b200_dmul + download per rank, one after the other" if pipe is None else
+                  ("per rank: top Strassen level on quadrant buffers (m4ri_b200_dmul_quads), quadrant shares uploaded, "
+                   "all-gathered over NVLink in row/column groups and downloaded as the schedule needs them" if quads is not None else
+                   "upload + all_gather + m4ri_b200_dmul + download per rank, one after the other" if pipe is None else
                    f"K-chunk pipeline per rank ({pr * args.ksub} chunks of {l // (pr * args.ksub)} columns: uploads, NVLink "
                    f"all-gathers in row/column groups, products and downloads overlapped; m4ri_b200/shard.py)")}
 
@@ -779,7 +902,9 @@ def main():
     ap.add_argument("--pinned", action="store_true", help="only the pinned end-to-end leg")
     ap.add_argument("--grid", default="auto", choices=["auto", "rows"],
                     help="C partition over ranks: 'rows' = row-blocks only; 'auto' = two column blocks from 4 ranks on")
-    ap.add_argument("--serial-e2e", action="store_true", help="N > 1: end-to-end leg without the K-chunk pipeline")
+    ap.add_argument("--e2e-mode", default="hooks", choices=["hooks", "kchunk", "serial"],
+                    help="N > 1 end to end: 'hooks' = quadrants of the top Strassen level uploaded / all-gathered / downloaded as the "
+                         "schedule needs them; 'kchunk' = K-chunk pipeline (m4ri_b200/shard.py); 'serial' = one after the other")
     ap.add_argument("--ksub", type=int, default=1, help="N > 1 end to end: sub-chunks per B row-slice (K-chunks = pr * ksub)")
     ap.add_argument("--chunk-levels", type=int, default=-1, help="N > 1 end to end: Strassen levels of a chunk product (-1: library rule)")
     ap.add_argument("--no-check", action="store_true", help="skip the verification after the timed legs")

@@ -148,6 +148,19 @@ void m4ri_b200_sync(void *stream);
  * clear != 0 computes C = A*B, clear == 0 computes C ^= A*B. */
 void m4ri_b200_dmul_m4rm(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int clear, void *stream);
 void m4ri_b200_dmul(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int cutoff, int clear, void *stream);
+/* C = A*B (clear) or C ^= A*B on explicit top-level quadrants (order 11, 12, 21, 22; each may be its own
+ * allocation) with transfer hooks called while the Strassen-Winograd schedule is enqueued: need_a/b/c(q) before the
+ * first kernel that reads quadrant q of A / B / C-as-addend, done_c(q) after the last kernel that writes quadrant q
+ * of C.  Used by the multi-rank end-to-end path to overlap uploads, NVLink exchanges and downloads with compute. */
+typedef struct m4ri_b200_hooks {
+  void (*need_a)(void *user, int q);
+  void (*need_b)(void *user, int q);
+  void (*need_c)(void *user, int q);
+  void (*done_c)(void *user, int q);
+  void *user;
+} m4ri_b200_hooks;
+void m4ri_b200_dmul_quads(m4ri_b200_dmat *const C[4], m4ri_b200_dmat const *const A[4], m4ri_b200_dmat const *const B[4],
+                          int cutoff, int clear, void *stream, m4ri_b200_hooks const *hooks);
 /* as dmul with the Strassen depth given explicitly (0 = leaf only); for cutoff sweeps. */
 void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int levels, int clear, void *stream);
 /* T X = B (left != 0) or X T = B (left == 0) on device matrices, T lower triangular or upper if

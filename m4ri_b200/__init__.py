@@ -55,6 +55,14 @@ class DMat(ctypes.Structure):
 
 DMatP = POINTER(DMat)
 
+HookFn = ctypes.CFUNCTYPE(None, c_void_p, c_int)
+
+
+class Hooks(ctypes.Structure):
+    """``m4ri_b200_hooks``: transfer callbacks of ``m4ri_b200_dmul_quads``."""
+
+    _fields_ = [("need_a", HookFn), ("need_b", HookFn), ("need_c", HookFn), ("done_c", HookFn), ("user", c_void_p)]
+
 _lib = None
 
 
@@ -96,6 +104,10 @@ def _declare(lib):
     lib.m4ri_b200_dmul_m4rm.argtypes = [DMatP, DMatP, DMatP, c_int, c_void_p]
     lib.m4ri_b200_dmul.argtypes = [DMatP, DMatP, DMatP, c_int, c_int, c_void_p]
     lib.m4ri_b200_dmul_levels.argtypes = [DMatP, DMatP, DMatP, c_int, c_int, c_void_p]
+    lib.m4ri_b200_dmul_quads.argtypes = [DMatP * 4, DMatP * 4, DMatP * 4, c_int, c_int, c_void_p, POINTER(Hooks)]
+    lib.m4ri_b200_result_free.argtypes = [MzdP]
+    for name in ("_mzd_mul_mp4", "_mzd_addmul_mp4"):
+        getattr(lib, name).argtypes, getattr(lib, name).restype = three, MzdP
     lib.m4ri_b200_dtranspose.argtypes = [DMatP, DMatP, c_void_p]
     lib.m4ri_b200_transpose.argtypes, lib.m4ri_b200_transpose.restype = [MzdP, MzdP], MzdP
     lib.m4ri_b200_dadd.argtypes = [DMatP, DMatP, DMatP, c_void_p]

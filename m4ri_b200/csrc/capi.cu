@@ -35,7 +35,7 @@ static_assert(offsetof(mzd_t, nrows) == 0 && offsetof(mzd_t, ncols) == 4 && offs
 namespace {
 
 constexpr uint8_t kFlagExcess = 0x2, kFlagWindow = 0x4;
-constexpr int kBuiltinCutoff = 8192;   // device Strassen leaf size; tuned on B200, see DESIGN.md
+constexpr int kBuiltinCutoff = 4096;   // device Strassen leaf size (4096-row leaves, 49 per launch); tuned on B200, see DESIGN.md
 
 struct Ctx {
   bool         ready = false;
@@ -671,6 +671,42 @@ void m4ri_b200_dmul(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat c
   cutoff = norm_cutoff(cutoff, "m4ri_b200_dmul");
   int const levels = A->ncols > 0 ? strassen_levels(A->nrows, A->ncols, B->ncols, cutoff) : 0;
   device_product(C, A, B, levels, clear != 0, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+}
+
+// Device product on explicit top-level quadrants with caller-supplied transfer hooks: the multi-rank end-to-end
+// path (bench.py --gpus N) keeps each quadrant of its operands in its own contiguous buffer, uploads / all-gathers
+// a quadrant when the schedule first needs it (need_*) and downloads a result quadrant as soon as it is final
+// (done_c).  The hooks are called on the calling thread while the schedule is being enqueued on `stream`.
+namespace {
+struct CallbackHooks : TopHooks {
+  m4ri_b200_hooks const *h;
+  explicit CallbackHooks(m4ri_b200_hooks const *h_) : h(h_) {}
+  void need_a(int q) override { if (h && h->need_a) h->need_a(h->user, q); }
+  void need_b(int q) override { if (h && h->need_b) h->need_b(h->user, q); }
+  void need_c(int q) override { if (h && h->need_c) h->need_c(h->user, q); }
+  void done_c(int q) override { if (h && h->done_c) h->done_c(h->user, q); }
+};
+}  // namespace
+
+void m4ri_b200_dmul_quads(m4ri_b200_dmat *const C[4], m4ri_b200_dmat const *const A[4], m4ri_b200_dmat const *const B[4],
+                          int cutoff, int clear, void *stream, m4ri_b200_hooks const *hooks) {
+  M4B_LOCKED;
+  Ctx &c = ctx();
+  int const m2 = A[0]->nrows, k2 = A[0]->ncols, n2 = B[0]->ncols;
+  for (int q = 0; q < 4; ++q)
+    if (A[q]->nrows != m2 || A[q]->ncols != k2 || B[q]->nrows != k2 || B[q]->ncols != n2 || C[q]->nrows != m2 || C[q]->ncols != n2)
+      die("m4ri_b200_dmul_quads: the four quadrants of an operand must have identical, matching shapes\n");
+  cutoff = norm_cutoff(cutoff, "m4ri_b200_dmul_quads");
+  int levels = strassen_levels(2 * m2, 2 * k2, 2 * n2, cutoff);
+  if (levels < 1) levels = 1;
+  if (m2 % (1 << (levels - 1)) || k2 % (128 << (levels - 1)) || n2 % (128 << (levels - 1)))
+    die("m4ri_b200_dmul_quads: quadrant dimensions must be multiples of 2^(levels-1) rows and 128 * 2^(levels-1) columns\n");
+  snprintf(c.last_path, sizeof c.last_path, "strassen:%d", levels);
+  c.ws.reserve(strassen_workspace_bytes(2 * m2, 2 * k2, 2 * n2, levels) + 3 * Workspace::bytes_for(m2, k2 > n2 ? k2 : n2));
+  DView a[4], b[4], cc[4];
+  for (int q = 0; q < 4; ++q) { a[q] = as_view(A[q]); b[q] = as_view(B[q]); cc[q] = as_view(C[q]); }
+  CallbackHooks hk(hooks);
+  strassen_mul_quads(cc, a, b, levels, clear != 0, c.ws, stream ? static_cast<cudaStream_t>(stream) : c.stream, hk);
 }
 
 void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int levels, int clear,

@@ -104,6 +104,9 @@ struct TopHooks {
 };
 void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s,
                   TopHooks *hooks = nullptr);
+// top level (levels >= 1) on explicit quadrants 11, 12, 21, 22, each possibly its own allocation
+void strassen_mul_quads(DView const c[4], DView const a[4], DView const b[4], int levels, bool clear, Workspace &ws,
+                        cudaStream_t s, TopHooks &hooks);
 
 // ---- triangular solve, left variants (trsm.cu) -----------------------------------------------
 // T: m x m (strict triangle read, unit diagonal implied), B: m x n, X overwrites B.

@@ -17,6 +17,10 @@ bool Stager::pageable(void const *p) {
 
 void Stager::ensure() {
   if (ready_) return;
+  if (char const *env = getenv("M4RI_B200_STAGE_THREADS")) {
+    int const t = atoi(env);
+    if (t >= 1 && t <= kMaxThreads) kThreads = t;
+  }
   for (int i = 0; i < kSlots; ++i) {
     M4B_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&slot_[i]), kChunkBytes, cudaHostAllocPortable));
     M4B_CUDA(cudaEventCreateWithFlags(&done_[i], cudaEventDisableTiming));

@@ -37,7 +37,8 @@ class Stager {
  private:
   static constexpr size_t kChunkBytes = 8u << 20;
   static constexpr int    kSlots = 4;
-  static constexpr int    kThreads = 4;
+  static constexpr int    kMaxThreads = 16;
+  int kThreads = 4;                 // copy threads incl. the caller ($M4RI_B200_STAGE_THREADS, read once in ensure())
 
   void ensure();
   void parallel_rows(size_t rows, std::function<void(size_t, size_t)> const &fn);

@@ -25,14 +25,18 @@ namespace m4b {
 // split while the half-problem keeps at least (2/3*cutoff)^3 bit-triples and every dimension of it
 // stays >= kMinLeafDim.  Depth never changes a result bit.
 static constexpr int kMinLeafDim = 2048;
+static constexpr int kTallRows   = 4096;   // rows of the tall-tile leaf: the recursion keeps m at or above it
 
 int strassen_levels(int m, int k, int n, int cutoff) {
   double const min_volume = (2.0 / 3.0 * cutoff) * (2.0 / 3.0 * cutoff) * (2.0 / 3.0 * cutoff);
   int const min_dim = cutoff < kMinLeafDim ? (cutoff * 2 / 3 > 64 ? cutoff * 2 / 3 : 64) : kMinLeafDim;
+  // with a production-size cutoff the leaves keep the 4096 rows the tall-tile kernel wants (a 2048-row leaf runs
+  // on the 1024-row kernel at 0.88 of its rate and cannot be batched 49 to a launch)
+  int const min_rows = cutoff >= kTallRows ? kTallRows : min_dim;
   int levels = 0;
   while (true) {
     int const m2 = (m + 1) / 2, k2 = (k + 1) / 2, n2 = (n + 1) / 2;
-    if (m2 < min_dim || k2 < (min_dim < 128 ? 128 : min_dim) || n2 < (min_dim < 128 ? 128 : min_dim)) break;
+    if (m2 < min_rows || k2 < (min_dim < 128 ? 128 : min_dim) || n2 < (min_dim < 128 ? 128 : min_dim)) break;
     if ((double)m2 * k2 * n2 < min_volume) break;
     m = m2; k = k2; n = n2;
     ++levels;
@@ -176,13 +180,21 @@ void strassen_mul(DView C, DView A, DView B, int levels, bool clear, Workspace &
     for (int q = 0; q < 4; ++q) hk.done_c(q);
     return;
   }
-  int const m2 = A.nrows / 2, k2 = A.ncols / 2, n2 = B.ncols / 2;
-  DView const a11 = A.sub(0, 0, m2, k2), a12 = A.sub(0, k2, m2, 2 * k2);
-  DView const a21 = A.sub(m2, 0, 2 * m2, k2), a22 = A.sub(m2, k2, 2 * m2, 2 * k2);
-  DView const b11 = B.sub(0, 0, k2, n2), b12 = B.sub(0, n2, k2, 2 * n2);
-  DView const b21 = B.sub(k2, 0, 2 * k2, n2), b22 = B.sub(k2, n2, 2 * k2, 2 * n2);
-  DView const c11 = C.sub(0, 0, m2, n2), c12 = C.sub(0, n2, m2, 2 * n2);
-  DView const c21 = C.sub(m2, 0, 2 * m2, n2), c22 = C.sub(m2, n2, 2 * m2, 2 * n2);
+  DView a[4], b[4], c[4];
+  quadrants(A, a);
+  quadrants(B, b);
+  quadrants(C, c);
+  strassen_mul_quads(c, a, b, levels, clear, ws, s, hk);
+}
+
+// The top level on explicit quadrants (order 11, 12, 21, 22; they need not be parts of one allocation: the
+// multi-rank end-to-end path keeps every quadrant in its own contiguous buffer so that NCCL can all-gather it).
+void strassen_mul_quads(DView const c[4], DView const a[4], DView const b[4], int levels, bool clear, Workspace &ws,
+                        cudaStream_t s, TopHooks &hk) {
+  int const m2 = a[0].nrows, k2 = a[0].ncols, n2 = b[0].ncols;
+  DView const a11 = a[0], a12 = a[1], a21 = a[2], a22 = a[3];
+  DView const b11 = b[0], b12 = b[1], b21 = b[2], b22 = b[3];
+  DView const c11 = c[0], c12 = c[1], c21 = c[2], c22 = c[3];
 
   size_t const mark = ws.mark();
   int const lv = levels - 1;
