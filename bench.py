@@ -269,7 +269,7 @@ def run_own_arm(args):
     if m % (128 * world) or l % (128 * world) or n % (128 * world):
         raise SystemExit("m, l, n must be multiples of 128 * gpus")
     cutoff = args.cutoff
-    # C is cut into pr row-blocks x pc column-blocks (pc = 2 from 4 ranks on, see m4ri_b200/shard.py):
+    # C is cut into pr row-blocks x pc column-blocks (2 x world/2 from 4 ranks on, see m4ri_b200/shard.py):
     # this rank owns C[rows gr, cols gc] = A[rows gr, :] * B[:, cols gc]
     pr, pc = shard.grid_shape(world, args.grid)
     gr, gc = shard.grid_coords(rank, world, args.grid)
@@ -901,7 +901,7 @@ def main():
     ap.add_argument("--pageable", action="store_true", help="only the pageable end-to-end leg")
     ap.add_argument("--pinned", action="store_true", help="only the pinned end-to-end leg")
     ap.add_argument("--grid", default="auto", choices=["auto", "rows"],
-                    help="C partition over ranks: 'rows' = row-blocks only; 'auto' = two column blocks from 4 ranks on")
+                    help="C partition over ranks: 'rows' = row-blocks only; 'auto' = 2 row-blocks x world/2 column blocks from 4 ranks on")
     ap.add_argument("--e2e-mode", default="hooks", choices=["hooks", "kchunk", "serial"],
                     help="N > 1 end to end: 'hooks' = quadrants of the top Strassen level uploaded / all-gathered / downloaded as the "
                          "schedule needs them; 'kchunk' = K-chunk pipeline (m4ri_b200/shard.py); 'serial' = one after the other")

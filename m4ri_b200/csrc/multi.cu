@@ -1,8 +1,8 @@
 // multi.cu — mzd_mul_mp / mzd_addmul_mp on several GPUs of one box, in ONE process.
 //
 // The reference's block-parallel multiply cuts C 2 x 2 over four OpenMP sections (m4ri/mp.c:158-275, the
-// split :179-228).  Here C is cut into pr x pc blocks, one per GPU (pc = 2 from four GPUs on — the reference's
-// shape — so that the per-GPU product stays close to a cube): GPU (gr, gc) owns
+// split :179-228).  Here C is cut into pr x pc blocks, one per GPU (2 x G/2 from four GPUs on — at four GPUs the
+// reference's 2 x 2 shape — so that the per-GPU product keeps half of the rows and the 4096-row leaves): GPU (gr, gc) owns
 //     C[rows gr, cols gc] (^)= A[rows gr, :] * B[:, cols gc].
 // Every operand bit crosses PCIe ONCE per box and the rest travels over NVLink: the pr GPUs of a column group
 // each upload 1/pr of B[:, cols gc] (a row-slice), the pc GPUs of a row group each upload 1/pc of the rows of
@@ -125,7 +125,9 @@ void multi_release() {
 }
 
 void multi_grid(int G, int n, int *pr, int *pc) {
-  *pc = (G >= 4 && G % 2 == 0 && n >= 256) ? 2 : 1;
+  // two row-blocks x G/2 column blocks from four GPUs on: the local product keeps half of the rows, and with them
+  // the 4096-row leaves of one more Strassen level (m4ri_b200/shard.py: grid_shape)
+  *pc = (G >= 4 && G % 2 == 0 && n >= 128 * (G / 2)) ? G / 2 : 1;
   *pr = G / *pc;
 }
 

@@ -5,12 +5,12 @@ starts with a 1/world row-slice of B and the slices are all-gathered once (NCCL 
 GPU box, gloo in the CPU tests).  The same split, inside one process, is implemented in C++ in
 csrc/multi.cu (mzd_mul_mp); the reference's own block-parallel scheme is m4ri/mp.c:158-275.
 
-From 4 ranks on the row-blocks are additionally cut into two COLUMN blocks (grid pr x 2): rank
-(gr, gc) owns C[rows gr, cols gc] = A[rows gr, :] * B[:, cols gc], starts with row-slice gr of
-B[:, cols gc] (still 1/world of B) and all-gathers only inside its column group (the pr ranks that
-share gc).  Same bits; the local product is closer to a cube (8 GPUs: 16384 x 65536 x 32768 instead of
-8192 x 65536 x 65536), so the same Strassen depth ends in 4096-row leaves — the tall-tile M4RM kernel —
-and each rank receives 3/16 instead of 7/8 of B.
+From 4 ranks on C is cut into a grid of 2 row-blocks x world/2 COLUMN blocks: rank (gr, gc) owns
+C[rows gr, cols gc] = A[rows gr, :] * B[:, cols gc], starts with row-slice gr of B[:, cols gc] (still
+1/world of B) and all-gathers only inside its column group (the pr ranks that share gc).  Same bits; the
+local product keeps 32768 rows (8 GPUs: 32768 x 65536 x 16384 instead of 8192 x 65536 x 65536), so the
+Strassen recursion still reaches 4096-row leaves — the tall-tile M4RM kernel, 49 products per launch —
+after three levels.
 
 The local multiply and the collective are passed in, so this module carries no compute and no
 device dependency.
@@ -49,10 +49,13 @@ def sharded_product(rank: int, world: int, a_block, b_slice, all_gather: Callabl
 # ---- 2D grid (pr row-blocks x pc column-blocks of C) -----------------------------------------
 
 def grid_shape(world: int, mode: str = "auto") -> Tuple[int, int]:
-    """(pr, pc).  'rows': pure row-blocks; 'auto': two column blocks from 4 ranks on (even world only)."""
+    """(pr, pc).  'rows': pure row-blocks; 'auto': from 4 ranks on (even world only) TWO row-blocks x world/2 column
+    blocks: the tall-tile leaf wants 4096-row operands, so the local product keeps half of the rows and with them all
+    but one of the Strassen levels of the one-GPU product (8 ranks: 32768 x 65536 x 16384 per rank, three levels,
+    where 4 row-blocks x 2 column blocks — 16384 x 65536 x 32768 — would stop at two)."""
     if mode not in ("auto", "rows"):
         raise ValueError(mode)
-    pc = 2 if mode == "auto" and world >= 4 and world % 2 == 0 else 1
+    pc = world // 2 if mode == "auto" and world >= 4 and world % 2 == 0 else 1
     return world // pc, pc
 
 

@@ -91,10 +91,10 @@ def test_sharded_product_over_gloo(world, shape):
     assert q.get(timeout=10) is True
 
 
-# ---- 2D grid (world >= 4): row-blocks x two column blocks, all-gather inside each column group -----------
+# ---- 2D grid (world >= 4): two row-blocks x world/2 column blocks, all-gather inside each column group ----
 
 def test_grid_helpers():
-    assert [shard.grid_shape(w) for w in (1, 2, 3, 4, 6, 8)] == [(1, 1), (2, 1), (3, 1), (2, 2), (3, 2), (4, 2)]
+    assert [shard.grid_shape(w) for w in (1, 2, 3, 4, 6, 8)] == [(1, 1), (2, 1), (3, 1), (2, 2), (2, 3), (2, 4)]
     assert shard.grid_shape(8, "rows") == (8, 1)
     for world in (4, 6, 8):
         pr, pc = shard.grid_shape(world)
