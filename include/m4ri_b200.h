@@ -88,6 +88,19 @@ void _mzd_trsm_lower_right(mzd_t const *L, mzd_t *B, const int cutoff);
 void mzd_trsm_upper_right(mzd_t const *U, mzd_t *B, const int cutoff);
 void _mzd_trsm_upper_right(mzd_t const *U, mzd_t *B, const int cutoff);
 
+/* PLE decomposition A = P L E in place, with the matrix resident in HBM for the whole factorisation (the recursion,
+ * its triangular solves and its Schur updates never leave the GPU): E above, L compressed into the first `rank`
+ * columns below, P as row transpositions (P->values[i] = row swapped with row i), Q->values[i] = column of the i-th
+ * pivot.  Same pivot rule as the reference, hence the same bits, P, rank and Q[0..rank).  m4ri/ple.h (mzd_ple,
+ * _mzd_ple), ple.c:33-178.  The reference's _mzd_pluq / mzd_echelonize_pluq / solve call _mzd_ple through the PLT and
+ * are captured with it when this library is preloaded. */
+typedef struct mzp_t {     /* m4ri/mzp.h:37-49 */
+  rci_t *values;
+  rci_t  length;
+} mzp_t;
+rci_t mzd_ple(mzd_t *A, mzp_t *P, mzp_t *Q, const int cutoff);
+rci_t _mzd_ple(mzd_t *A, mzp_t *P, mzp_t *Q, const int cutoff);
+
 /* ---- Part 2: extension API --------------------------------------------------------- */
 
 /* Library / device control. */
@@ -162,6 +175,8 @@ typedef struct m4ri_b200_hooks {
 void m4ri_b200_dmul_quads(m4ri_b200_dmat *const C[4], m4ri_b200_dmat const *const A[4], m4ri_b200_dmat const *const B[4],
                           int cutoff, int clear, void *stream, m4ri_b200_hooks const *hooks);
 /* as dmul with the Strassen depth given explicitly (0 = leaf only); for cutoff sweeps. */
+/* PLE of a device-resident matrix in place; P (nrows ints) and Q (ncols ints) are host arrays; returns the rank */
+rci_t m4ri_b200_dple(m4ri_b200_dmat *A, rci_t *P, rci_t *Q, void *stream);
 void m4ri_b200_dmul_levels(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, int levels, int clear, void *stream);
 /* T X = B (left != 0) or X T = B (left == 0) on device matrices, T lower triangular or upper if
  * upper != 0; X overwrites B. */

@@ -55,6 +55,15 @@ class DMat(ctypes.Structure):
 
 DMatP = POINTER(DMat)
 
+
+class MzpT(ctypes.Structure):
+    """``mzp_t`` (m4ri/mzp.h:37-49): a permutation as LAPACK-style transpositions."""
+
+    _fields_ = [("values", POINTER(c_int)), ("length", c_int)]
+
+
+MzpP = POINTER(MzpT)
+
 HookFn = ctypes.CFUNCTYPE(None, c_void_p, c_int)
 
 
@@ -106,6 +115,9 @@ def _declare(lib):
     lib.m4ri_b200_dmul_levels.argtypes = [DMatP, DMatP, DMatP, c_int, c_int, c_void_p]
     lib.m4ri_b200_dmul_quads.argtypes = [DMatP * 4, DMatP * 4, DMatP * 4, c_int, c_int, c_void_p, POINTER(Hooks)]
     lib.m4ri_b200_result_free.argtypes = [MzdP]
+    for name in ("mzd_ple", "_mzd_ple"):
+        getattr(lib, name).argtypes, getattr(lib, name).restype = [MzdP, MzpP, MzpP, c_int], c_int
+    lib.m4ri_b200_dple.argtypes, lib.m4ri_b200_dple.restype = [DMatP, POINTER(c_int), POINTER(c_int), c_void_p], c_int
     for name in ("_mzd_mul_mp4", "_mzd_addmul_mp4"):
         getattr(lib, name).argtypes, getattr(lib, name).restype = three, MzdP
     lib.m4ri_b200_dtranspose.argtypes = [DMatP, DMatP, c_void_p]

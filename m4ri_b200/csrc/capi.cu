@@ -512,6 +512,37 @@ mzd_t *_mzd_addmul_mp4(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff) {
   return C;
 }
 
+// ---- widened rows: PLE with the matrix resident on the device (ple.cu) -----------------------------------
+rci_t _mzd_ple(mzd_t *A, mzp_t *P, mzp_t *Q, int const cutoff) {
+  M4B_LOCKED;
+  rci_t const m = A->nrows, n = A->ncols;
+  if (m == 0 || n == 0) {
+    for (rci_t i = 0; i < m; ++i) P->values[i] = i;
+    for (rci_t i = 0; i < n; ++i) Q->values[i] = i;
+    return 0;
+  }
+  Ctx &c = ctx();
+  ++g_products;
+  snprintf(c.last_path, sizeof c.last_path, "ple");
+  int const co = norm_cutoff(cutoff < 0 ? 0 : cutoff, "_mzd_ple");
+  c.ws.reserve(Workspace::bytes_for(m, n) + ple_workspace_bytes(m, n, co));
+  cudaStream_t s = c.stream;
+  DView dA = c.ws.alloc(m, n);
+  zero_async(dA, s);
+  upload(dA, A, s, &c.stager);
+  rci_t const rank = ple_device(dA, P->values, Q->values, co, c.ws, s);
+  download(A, dA, s, c.host_tmp, &c.stager);
+  M4B_CUDA(cudaStreamSynchronize(s));
+  c.ws.release(0);
+  return rank;
+}
+
+rci_t mzd_ple(mzd_t *A, mzp_t *P, mzp_t *Q, int const cutoff) {   // m4ri/ple.c:33-39
+  if (P->length != A->nrows) die("mzd_ple: Permutation P length (%d) must match A nrows (%d)\n", P->length, A->nrows);
+  if (Q->length != A->ncols) die("mzd_ple: Permutation Q length (%d) must match A ncols (%d)\n", Q->length, A->ncols);
+  return _mzd_ple(A, P, Q, cutoff);
+}
+
 // ---- Part 2: extension API ------------------------------------------------------------------
 
 int m4ri_b200_version(void) { return 100; }
@@ -817,6 +848,15 @@ mzd_t *m4ri_b200_inv_m4ri(mzd_t *B, mzd_t const *A) {
   m4ri_b200_mzd_free(I);
   c.ws.release(0);
   return B;
+}
+
+rci_t m4ri_b200_dple(m4ri_b200_dmat *A, rci_t *P, rci_t *Q, void *stream) {
+  M4B_LOCKED;
+  Ctx &c = ctx();
+  snprintf(c.last_path, sizeof c.last_path, "ple");
+  int const co = norm_cutoff(0, "m4ri_b200_dple");
+  c.ws.reserve(ple_workspace_bytes(A->nrows, A->ncols, co));
+  return ple_device(as_view(A), P, Q, co, c.ws, stream ? static_cast<cudaStream_t>(stream) : c.stream);
 }
 
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {

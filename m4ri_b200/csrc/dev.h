@@ -118,4 +118,9 @@ size_t trsm_workspace_bytes(int t, int m, int n, int cutoff);
 int    echelonize_device(DView A, Workspace &ws, cudaStream_t s);     // in place, returns the rank, synchronises s
 size_t echelon_workspace_bytes(int m, int n, int64_t pitch_words = 0);   // pitch_words: A's pitch if above the minimal one
 
+// ---- PLE decomposition (ple.cu) ----------------------------------------------------------------
+// in place on a device-resident matrix; P (nrows ints) and Q (ncols ints) on the host; returns the rank, synchronises s
+int    ple_device(DView A, int *P, int *Q, int cutoff, Workspace &ws, cudaStream_t s);
+size_t ple_workspace_bytes(int m, int n, int cutoff);
+
 }  // namespace m4b

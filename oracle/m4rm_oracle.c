@@ -550,3 +550,64 @@ orc_rci orc_echelonize(orc_mzd *M, int full) {
   }
   return pivots;
 }
+
+/* ---- PLE decomposition (m4ri/ple.c:222-272 _mzd_ple_naive) ------------------------------------------------
+ * A = P L E in place: leftmost column with a 1 at or below row_pos, FIRST row with it (in the current, already
+ * swapped order) becomes the pivot: P[row_pos] = that row, Q[row_pos] = the column, rows swapped, and the pivot
+ * row is added to every lower row with a 1 in the column FROM THE NEXT COLUMN ON (the 1 stays as the L entry).
+ * Afterwards P[i] = i and Q[i] = i for i >= rank and L is compressed: for j < rank column Q[j] is swapped into
+ * column j in rows j.. (mzd_col_swap_in_rows).  Every PLE variant of the reference (naive, russian, recursive
+ * with any cutoff) produces exactly these bits, P and Q[0..rank) — pinned by tests/test_ple_oracle.py. */
+static int orc_bit(orc_mzd const *M, orc_rci r, orc_rci c) { return (int)((rowp(M, r)[c / RADIX] >> (c % RADIX)) & 1); }
+
+orc_rci orc_ple(orc_mzd *A, orc_rci *P, orc_rci *Q) {
+  orc_rci row_pos = 0, col_pos = 0;
+  while (row_pos < A->nrows && col_pos < A->ncols) {
+    int found = 0;
+    orc_rci i = 0, j = 0;
+    for (j = col_pos; j < A->ncols && !found; ++j)
+      for (i = row_pos; i < A->nrows; ++i)
+        if (orc_bit(A, i, j)) { found = 1; break; }
+    if (!found) break;
+    --j;                                                /* the loop header advanced it once more */
+    P[row_pos] = i;
+    Q[row_pos] = j;
+    if (i != row_pos) {                                 /* mzd_row_swap */
+      orc_word *a = rowp(A, row_pos), *b = rowp(A, i);
+      for (orc_wi w = 0; w < A->width; ++w) {
+        orc_word const mask = (w == A->width - 1) ? A->high_bitmask : ~(orc_word)0;
+        orc_word const t = (a[w] ^ b[w]) & mask;
+        a[w] ^= t;
+        b[w] ^= t;
+      }
+    }
+    if (j + 1 < A->ncols) {
+      orc_word const *src = rowp(A, row_pos);
+      for (orc_rci l = row_pos + 1; l < A->nrows; ++l) {
+        if (!orc_bit(A, l, j)) continue;
+        orc_word *dst = rowp(A, l);                     /* mzd_row_add_offset(A, l, row_pos, j + 1) */
+        orc_rci const c0 = j + 1;
+        for (orc_wi w = c0 / RADIX; w < A->width; ++w) {
+          orc_word mask = (w == A->width - 1) ? A->high_bitmask : ~(orc_word)0;
+          if (w == c0 / RADIX) mask &= ~(orc_word)0 << (c0 % RADIX);
+          dst[w] ^= src[w] & mask;
+        }
+      }
+    }
+    ++row_pos;
+    col_pos = j + 1;
+  }
+  for (orc_rci i = row_pos; i < A->nrows; ++i) P[i] = i;
+  for (orc_rci i = row_pos; i < A->ncols; ++i) Q[i] = i;
+  for (orc_rci j = 0; j < row_pos; ++j) {               /* compress L */
+    if (Q[j] <= j) continue;
+    for (orc_rci r = j; r < A->nrows; ++r) {
+      int const a = orc_bit(A, r, j), b = orc_bit(A, r, Q[j]);
+      if (a != b) {
+        rowp(A, r)[j / RADIX] ^= (orc_word)1 << (j % RADIX);
+        rowp(A, r)[Q[j] / RADIX] ^= (orc_word)1 << (Q[j] % RADIX);
+      }
+    }
+  }
+  return row_pos;
+}

@@ -70,6 +70,10 @@ orc_mzd *orc_transpose(orc_mzd *DST, orc_mzd const *A);
 /* m4ri/mzd.c:208-233: (reduced) row echelon form in place, returns the rank */
 orc_rci  orc_echelonize(orc_mzd *M, int full);
 
+/* m4ri/ple.c:222-272: A = P L E in place (L compressed into the first rank columns); P has nrows entries,
+ * Q ncols; returns the rank */
+orc_rci  orc_ple(orc_mzd *A, orc_rci *P, orc_rci *Q);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,7 @@ def oracle():
         lib.orc_trsm_upper_right.argtypes = [MzdP, MzdP]
         lib.orc_transpose.argtypes, lib.orc_transpose.restype = [MzdP, MzdP], MzdP
         lib.orc_echelonize.argtypes, lib.orc_echelonize.restype = [MzdP, c_int], c_int
+        lib.orc_ple.argtypes, lib.orc_ple.restype = [MzdP, POINTER(c_int), POINTER(c_int)], c_int
         _oracle = lib
     return _oracle
 
@@ -201,9 +202,10 @@ def block_digest(words2d: np.ndarray) -> str:
     return h.hexdigest()
 
 
-# C of every large case is recorded as 8 row-blocks x 2 column-blocks, so that every rank of a
-# 1/2/4/8-GPU partition (row-blocks, or pr x 2 grid) can check its own block against the reference.
-LARGE_BLOCK_ROWS, LARGE_BLOCK_COLS = 8, 2
+# C of every large case is recorded as 8 row-blocks x 8 column-blocks, so that every rank of a
+# 1/2/4/8-GPU partition (row-blocks, or any pr x pc grid with pr, pc dividing 8) can check its own block
+# against the reference.
+LARGE_BLOCK_ROWS, LARGE_BLOCK_COLS = 8, 8
 
 
 def large_block_digests(words2d: np.ndarray) -> list:
