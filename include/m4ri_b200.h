@@ -101,6 +101,15 @@ typedef struct mzp_t {     /* m4ri/mzp.h:37-49 */
 rci_t mzd_ple(mzd_t *A, mzp_t *P, mzp_t *Q, const int cutoff);
 rci_t _mzd_ple(mzd_t *A, mzp_t *P, mzp_t *Q, const int cutoff);
 
+/* Elimination entry points served by the device RREF (m4ri/echelonform.h, brilliantrussian.h:56; echelonform.c:30-36,
+ * brilliantrussian.c:603-967, 971-997).  full != 0: the reduced row echelon form (unique, bit-identical to the
+ * reference).  full == 0: handed on to the libm4ri that follows in the link order when there is one (its result
+ * depends on its k); stand-alone the reduced form is returned, which is a row echelon form as well.  Returns the rank.
+ * mzd_inv_m4ri: B = A^-1 as the right block of the RREF of [A | I]; B may be NULL. */
+rci_t  mzd_echelonize_m4ri(mzd_t *A, int full, int k);
+rci_t  mzd_echelonize(mzd_t *A, int full);
+mzd_t *mzd_inv_m4ri(mzd_t *B, mzd_t const *A, int k);
+
 /* ---- Part 2: extension API --------------------------------------------------------- */
 
 /* Library / device control. */

@@ -126,6 +126,9 @@ def _declare(lib):
     lib.m4ri_b200_dechelonize.argtypes, lib.m4ri_b200_dechelonize.restype = [DMatP, c_int, c_void_p], c_int
     lib.m4ri_b200_echelonize.argtypes, lib.m4ri_b200_echelonize.restype = [MzdP, c_int], c_int
     lib.m4ri_b200_inv_m4ri.argtypes, lib.m4ri_b200_inv_m4ri.restype = [MzdP, MzdP], MzdP
+    lib.mzd_echelonize_m4ri.argtypes, lib.mzd_echelonize_m4ri.restype = [MzdP, c_int, c_int], c_int
+    lib.mzd_echelonize.argtypes, lib.mzd_echelonize.restype = [MzdP, c_int], c_int
+    lib.mzd_inv_m4ri.argtypes, lib.mzd_inv_m4ri.restype = [MzdP, MzdP, c_int], MzdP
     return lib
 
 

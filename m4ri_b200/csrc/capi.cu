@@ -543,6 +543,36 @@ rci_t mzd_ple(mzd_t *A, mzp_t *P, mzp_t *Q, int const cutoff) {   // m4ri/ple.c:
   return _mzd_ple(A, P, Q, cutoff);
 }
 
+// ---- widened rows: elimination entry points of libm4ri served by the device RREF (echelon.cu) -------------
+// m4ri/echelonform.c:30-36, m4ri/brilliantrussian.c:603-967, 971-997.  full != 0 asks for THE reduced row echelon form
+// (unique: bit-identical whatever the algorithm).  full == 0 asks for AN upper-triangular echelon form whose bits
+// depend on the reference's k and block sizes: when a libm4ri follows in the link order (preload / link-first
+// deployment) that call is handed on to it unchanged; stand-alone, the reduced form — itself a row echelon form — is
+// returned.
+typedef rci_t (*echelonize_m4ri_fn)(mzd_t *, int, int);
+typedef rci_t (*echelonize_fn)(mzd_t *, int);
+
+rci_t mzd_echelonize_m4ri(mzd_t *A, int full, int k) {
+  if (!full) {
+    static echelonize_m4ri_fn next = reinterpret_cast<echelonize_m4ri_fn>(dlsym(RTLD_NEXT, "mzd_echelonize_m4ri"));
+    if (next) return next(A, full, k);
+  }
+  return m4ri_b200_echelonize(A, 1);
+}
+
+rci_t mzd_echelonize(mzd_t *A, int full) {
+  if (!full) {
+    static echelonize_fn next = reinterpret_cast<echelonize_fn>(dlsym(RTLD_NEXT, "mzd_echelonize"));
+    if (next) return next(A, full);
+  }
+  return m4ri_b200_echelonize(A, 1);
+}
+
+mzd_t *mzd_inv_m4ri(mzd_t *B, mzd_t const *A, int k) {
+  (void)k;
+  return m4ri_b200_inv_m4ri(B, A);
+}
+
 // ---- Part 2: extension API ------------------------------------------------------------------
 
 int m4ri_b200_version(void) { return 100; }

@@ -18,7 +18,9 @@
 //     first row with the bit (block-wide minimum over the current order), swaps it up and eliminates below —
 //     every row's 128-bit strip word is updated by its own thread;
 //   * the host only composes permutations (it needs the ranks to cut the windows anyway).
+#include <cooperative_groups.h>
 #include <string.h>
+#include <time.h>
 
 #include <unordered_map>
 #include <vector>
@@ -141,6 +143,112 @@ __global__ void __launch_bounds__(kStripThreads) ple_strip_kernel(word *base, lo
   if (tid == 0) out->rank = rank;
 }
 
+// The same factorisation with the strip held in REGISTERS by a thread-block cluster: position p of the current row
+// order lives in slot p % kSlots of thread (p / kSlots) % kClThreads of CTA p / (kSlots * kClThreads), so an
+// elimination step is a few predicated XORs per thread instead of a sweep over global memory (the one-CTA kernel
+// above spends ~20 us per pivot on 65536 rows: every thread walks 64 strided 16-byte words through L2).  Per pivot
+// column: local first candidate -> warp / CTA minimum -> every CTA's leader stores its minimum into EVERY CTA's shared
+// memory (DSMEM) -> cluster barrier -> the owners of the pivot position and of position rpos publish their words the
+// same way -> cluster barrier -> swap + eliminate in registers.  Up to 8 x 512 x 16 = 65536 rows.
+constexpr int kClThreads = 512, kSlots = 16, kClMax = 8;
+constexpr int kInf = 0x7fffffff;
+
+__global__ void __launch_bounds__(kClThreads, 1) ple_strip_cluster_kernel(word *base, long long pitch, int nr, int nc, StripResult *out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  int const crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  __shared__ int s_warp[kClThreads / 32];
+  __shared__ int s_mins[2][kClMax];
+  __shared__ unsigned long long s_pw[2], s_rw[2];
+  __shared__ int s_Q[kStripCols];
+  int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int const p0 = (crank * kClThreads + tid) * kSlots;
+  U128 w[kSlots];
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) w[k] = p0 + k < nr ? ld128(base + (long long)(p0 + k) * pitch) : U128{0ull, 0ull};
+  int rpos = 0, par = 0;
+  for (int j = 0; j < nc && rpos < nr; ++j) {
+    int cand = kInf;
+#pragma unroll
+    for (int k = kSlots - 1; k >= 0; --k)
+      if (p0 + k >= rpos && bit128(w[k], j)) cand = p0 + k;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, off));
+    if (lane == 0) s_warp[warp] = cand;
+    __syncthreads();
+    if (warp == 0) {
+      int v = lane < kClThreads / 32 ? s_warp[lane] : kInf;
+#pragma unroll
+      for (int off = 16; off; off >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, off));
+      if (lane < csize) *cluster.map_shared_rank(&s_mins[par][crank], lane) = v;      // lane r stores into CTA r
+    }
+    cluster.sync();
+    int g = kInf;
+    for (int r = 0; r < csize; ++r) g = min(g, s_mins[par][r]);
+    par ^= 1;
+    if (g == kInf) continue;                         // no 1 in this column at or below rpos (every CTA agrees)
+    bool const own_g = g >= p0 && g < p0 + kSlots, own_r = rpos >= p0 && rpos < p0 + kSlots;
+    if (own_g || own_r) {
+      U128 vg{0ull, 0ull}, vr{0ull, 0ull};
+#pragma unroll
+      for (int k = 0; k < kSlots; ++k) {
+        if (p0 + k == g) vg = w[k];
+        if (p0 + k == rpos) vr = w[k];
+      }
+      for (int r = 0; r < csize; ++r) {
+        if (own_g) {
+          unsigned long long *d = cluster.map_shared_rank(s_pw, r);
+          d[0] = vg.lo;
+          d[1] = vg.hi;
+        }
+        if (own_r) {
+          unsigned long long *d = cluster.map_shared_rank(s_rw, r);
+          d[0] = vr.lo;
+          d[1] = vr.hi;
+        }
+      }
+    }
+    cluster.sync();
+    U128 const pw{s_pw[0], s_pw[1]}, rw{s_rw[0], s_rw[1]};
+    U128 const m = above(j);
+    unsigned long long const plo = pw.lo & m.lo, phi = pw.hi & m.hi;
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) {
+      int const p = p0 + k;
+      if (p == rpos) w[k] = pw;                      // the pivot row moves up ...
+      else if (p == g) w[k] = rw;                    // ... the row it displaces takes its place
+      if (p > rpos && bit128(w[k], j)) {
+        w[k].lo ^= plo;
+        w[k].hi ^= phi;
+      }
+    }
+    if (tid == 0) {
+      s_Q[rpos] = j;
+      if (crank == 0) {
+        out->P[rpos] = g;
+        out->Q[rpos] = j;
+      }
+    }
+    ++rpos;
+  }
+  __syncthreads();
+  int const rank = rpos;
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) {
+    int const p = p0 + k;
+    if (p >= nr) continue;
+    U128 v = w[k];
+    int const upto = p < rank - 1 ? p : rank - 1;
+    for (int jj = 0; jj <= upto; ++jj) {
+      int const q = s_Q[jj];
+      if (q > jj) v = swap_bits(v, jj, q);
+    }
+    st128(base + (long long)p * pitch, v);
+  }
+  if (crank == 0 && tid == 0) out->rank = rank;
+  cluster.sync();                                    // no CTA leaves while a peer could still address its shared memory
+}
+
 // rows: T[k] = M[src[k]] (GATHER) / M[dst[k]] = T[k] (scatter) over the words [w0, w0 + nw) — two launches apply a
 // row permutation to a column range
 template <bool GATHER>
@@ -188,6 +296,29 @@ __global__ void __launch_bounds__(256) compress_l_kernel(word *base, long long p
   }
 }
 
+// M4RI_B200_PLE_PROFILE=1: wall time per phase (the stream is synchronised after each, so the total grows a little)
+struct PleProfile {
+  bool   on = false;
+  double t[6] = {};     // strip, permute, trsm, update, compress, sync
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  }
+};
+PleProfile g_ple_prof;
+struct PhaseTimer {
+  int phase;
+  cudaStream_t s;
+  double t0 = 0;
+  PhaseTimer(int ph, cudaStream_t st) : phase(ph), s(st) { if (g_ple_prof.on) t0 = PleProfile::now(); }
+  ~PhaseTimer() {
+    if (!g_ple_prof.on) return;
+    cudaStreamSynchronize(s);
+    g_ple_prof.t[phase] += PleProfile::now() - t0;
+  }
+};
+
 struct PleCtx {
   DView        M;           // the whole device matrix
   Workspace   *ws;
@@ -211,6 +342,7 @@ void update(DView C, DView A, DView B, PleCtx &cx) {
 // padded right edge): the transpositions P[0..np) in order, composed on the host into one gather / scatter
 void apply_p_left(PleCtx &cx, int r0, int c_lo, int c_hi, int const *P, int np) {
   if (np <= 0 || c_hi <= c_lo) return;
+  PhaseTimer pt(1, cx.s);
   std::unordered_map<int, int> cur;                    // position -> row whose content sits there now
   auto at = [&](int pos) { auto it = cur.find(pos); return it == cur.end() ? pos : it->second; };
   for (int i = 0; i < np; ++i) {
@@ -253,8 +385,30 @@ int ple_rec(PleCtx &cx, int r0, int c0, int nr, int nc, int *P, int *Q) {
   for (int i = 0; i < nc; ++i) Q[i] = i;
   if (nr <= 0 || nc <= 0) return 0;
   if (nc <= kStripCols) {
+    PhaseTimer pt(0, cx.s);
     word *base = cx.M.data + (long long)r0 * cx.M.pitch + c0 / 64;
-    ple_strip_kernel<<<1, kStripThreads, 0, cx.s>>>(base, cx.M.pitch, nr, nc, cx.d_res);
+    static int const strip_variant = [] {            // M4RI_B200_PLE_STRIP=0: always the one-CTA global-memory kernel
+      char const *env = getenv("M4RI_B200_PLE_STRIP");
+      return env && env[0] == '0' ? 0 : 1;
+    }();
+    int const per_cta = kClThreads * kSlots;
+    if (strip_variant == 1 && nr <= kClMax * per_cta) {
+      int cl = 1;
+      while (cl * per_cta < nr) cl *= 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)cl);
+      cfg.blockDim = dim3(kClThreads);
+      cfg.stream = cx.s;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = (unsigned)cl;
+      attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      M4B_CUDA(cudaLaunchKernelEx(&cfg, ple_strip_cluster_kernel, base, (long long)cx.M.pitch, nr, nc, cx.d_res));
+    } else {
+      ple_strip_kernel<<<1, kStripThreads, 0, cx.s>>>(base, cx.M.pitch, nr, nc, cx.d_res);
+    }
     M4B_CUDA(cudaGetLastError());
     ++g_kernel_launches;
     M4B_CUDA(cudaMemcpyAsync(cx.h_res, cx.d_res, sizeof(StripResult), cudaMemcpyDeviceToHost, cx.s));
@@ -270,9 +424,14 @@ int ple_rec(PleCtx &cx, int r0, int c0, int nr, int nc, int *P, int *Q) {
   if (r1) {
     apply_p_left(cx, r0, c0 + n1, c_end, P, r1);          // mzd_apply_p_left(A1, P1)
     DView const A00 = M.sub(r0, c0, r0 + r1, c0 + r1), A01 = M.sub(r0, c0 + n1, r0 + r1, c_end);
-    trsm_left(A00, A01, false, cx.cutoff, *cx.ws, cx.s);  // _mzd_trsm_lower_left(A00, A01)
-    if (nr > r1)                                          // mzd_addmul(A11, A10, A01)
+    {
+      PhaseTimer pt(2, cx.s);
+      trsm_left(A00, A01, false, cx.cutoff, *cx.ws, cx.s);  // _mzd_trsm_lower_left(A00, A01)
+    }
+    if (nr > r1) {                                        // mzd_addmul(A11, A10, A01)
+      PhaseTimer pt(3, cx.s);
       update(M.sub(r0 + r1, c0 + n1, r0 + nr, c_end), M.sub(r0 + r1, c0, r0 + nr, c0 + r1), A01, cx);
+    }
   }
   int *P2 = P + r1, *Q2 = Q + n1;
   int const r2 = ple_rec(cx, r0 + r1, c0 + n1, nr - r1, nc - n1, P2, Q2);
@@ -282,6 +441,7 @@ int ple_rec(PleCtx &cx, int r0, int c0, int nr, int nc, int *P, int *Q) {
   for (int i = 0; i < nc - n1; ++i) Q2[i] += n1;
   for (int i = n1, j = r1; i < n1 + r2; ++i, ++j) Q[j] = Q[i];
   if (r1 != n1 && r2 > 0 && nr > r1) {                    // _mzd_compress_l(A, r1, n1, r2)
+    PhaseTimer pt(4, cx.s);
     word *base = M.data + (long long)r0 * M.pitch + c0 / 64;
     unsigned const blocks = (unsigned)((nr - r1 + 255) / 256);
     compress_l_kernel<<<blocks, 256, 0, cx.s>>>(base, M.pitch, nr, r1, n1, r2);
@@ -320,8 +480,13 @@ int ple_device(DView A, int *P, int *Q, int cutoff, Workspace &ws, cudaStream_t 
   cx.d_rows = reinterpret_cast<int *>(ws.alloc(1, (int)((cx.rows_cap * sizeof(int) + 255) / 256 * 256 * 8)).data);
   cx.d_res = reinterpret_cast<StripResult *>(ws.alloc(1, (int)((sizeof(StripResult) + 255) / 256 * 256 * 8)).data);
   M4B_CUDA(cudaMallocHost(reinterpret_cast<void **>(&cx.h_res), sizeof(StripResult)));
+  g_ple_prof.on = getenv("M4RI_B200_PLE_PROFILE") != nullptr;
+  for (double &t : g_ple_prof.t) t = 0;
   int const rank = ple_rec(cx, 0, 0, m, n, P, Q);
   M4B_CUDA(cudaStreamSynchronize(s));
+  if (g_ple_prof.on)
+    fprintf(stderr, "m4ri_b200 ple %d x %d: strip %.1f ms, permute %.1f ms, trsm %.1f ms, update %.1f ms, compress %.1f ms\n", m, n,
+            g_ple_prof.t[0] * 1e3, g_ple_prof.t[1] * 1e3, g_ple_prof.t[2] * 1e3, g_ple_prof.t[3] * 1e3, g_ple_prof.t[4] * 1e3);
   cudaFreeHost(cx.h_res);
   ws.release(mark);
   return rank;

@@ -409,3 +409,36 @@ def test_large_pageable_windows_go_through_the_staging_ring(lib, fn):
     getattr(lib, fn)(C, A, B, 2048)
     assert np.array_equal(H.storage(PC), H.storage(want_parent))
     H.free(A, B, C, Cw, PA, PB, PC, want_parent)
+
+
+def test_entry_points_from_four_host_threads(lib):
+    """an OpenMP libm4ri calls _mzd_mul_even / _mzd_addmul_even from four concurrent sections
+    (m4ri/mp.c:87-108) and those calls bind to this library under LD_PRELOAD: the context (workspace stack, staging
+    ring, streams) is serialised by a process-wide lock, so concurrent callers get correct products."""
+    import threading
+    H.libc.srandom(123)
+    jobs = []
+    for t in range(4):
+        m, l, n = 900 + 130 * t, 1100 + 64 * t, 700 + 257 * t
+        A, B, C = H.random_matrix(m, l), H.random_matrix(l, n), H.random_matrix(m, n)
+        want = H.oracle().orc_addmul(H.clone(C), A, B, 0)
+        jobs.append((A, B, C, want))
+    errors = []
+
+    def work(job, fn):
+        A, B, C, want = job
+        for _ in range(6):
+            D = H.clone(C)
+            getattr(lib, fn)(D, A, B, 256)
+            if not np.array_equal(H.storage(D), H.storage(want)):
+                errors.append(fn)
+            H.free(D)
+
+    threads = [threading.Thread(target=work, args=(job, fn)) for job, fn in zip(jobs, ["mzd_addmul", "_mzd_addmul_even", "_mzd_addmul_mp4", "mzd_addmul_m4rm"])]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for job in jobs:
+        H.free(*job)

