@@ -147,9 +147,10 @@ __global__ void __launch_bounds__(kStripThreads) ple_strip_kernel(word *base, lo
 // order lives in slot p % kSlots of thread (p / kSlots) % kClThreads of CTA p / (kSlots * kClThreads), so an
 // elimination step is a few predicated XORs per thread instead of a sweep over global memory (the one-CTA kernel
 // above spends ~20 us per pivot on 65536 rows: every thread walks 64 strided 16-byte words through L2).  Per pivot
-// column: local first candidate -> warp / CTA minimum -> every CTA's leader stores its minimum into EVERY CTA's shared
-// memory (DSMEM) -> cluster barrier -> the owners of the pivot position and of position rpos publish their words the
-// same way -> cluster barrier -> swap + eliminate in registers.  Up to 8 x 512 x 16 = 65536 rows.
+// column: local first candidate -> warp / CTA minimum -> the owner of every CTA's candidate stores (position, word)
+// into EVERY CTA's shared memory (DSMEM), the owner of position rpos its word -> ONE cluster barrier -> every thread
+// picks the global first candidate, swaps and eliminates in registers.  Up to 8 x 512 x 16 = 65536 rows.
+// Measured, 65536^2: 3306 ms with the one-CTA kernel, 486 ms with two barriers per column.
 constexpr int kClThreads = 512, kSlots = 16, kClMax = 8;
 constexpr int kInf = 0x7fffffff;
 
@@ -158,8 +159,13 @@ __global__ void __launch_bounds__(kClThreads, 1) ple_strip_cluster_kernel(word *
   cg::cluster_group cluster = cg::this_cluster();
   int const crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   __shared__ int s_warp[kClThreads / 32];
-  __shared__ int s_mins[2][kClMax];
-  __shared__ unsigned long long s_pw[2], s_rw[2];
+  struct Cand {
+    unsigned long long lo, hi;
+    int pos;
+    int pad;
+  };
+  __shared__ Cand s_cand[2][kClMax];                 // [parity][CTA]: each CTA's first candidate and its strip word
+  __shared__ unsigned long long s_rw[2][2];          // [parity]: the word at position rpos
   __shared__ int s_Q[kStripCols];
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int const p0 = (crank * kClThreads + tid) * kSlots;
@@ -168,48 +174,49 @@ __global__ void __launch_bounds__(kClThreads, 1) ple_strip_cluster_kernel(word *
   for (int k = 0; k < kSlots; ++k) w[k] = p0 + k < nr ? ld128(base + (long long)(p0 + k) * pitch) : U128{0ull, 0ull};
   int rpos = 0, par = 0;
   for (int j = 0; j < nc && rpos < nr; ++j) {
+    // ---- ONE cluster barrier per column: every CTA publishes (first candidate, its word) to every CTA, the owner
+    //      of position rpos publishes that word as well; after the barrier each thread knows pivot and both words ----
     int cand = kInf;
 #pragma unroll
     for (int k = kSlots - 1; k >= 0; --k)
       if (p0 + k >= rpos && bit128(w[k], j)) cand = p0 + k;
+    int const mine = cand;
 #pragma unroll
     for (int off = 16; off; off >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, off));
     if (lane == 0) s_warp[warp] = cand;
     __syncthreads();
-    if (warp == 0) {
-      int v = lane < kClThreads / 32 ? s_warp[lane] : kInf;
+    int bm = kInf;
 #pragma unroll
-      for (int off = 16; off; off >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, off));
-      if (lane < csize) *cluster.map_shared_rank(&s_mins[par][crank], lane) = v;      // lane r stores into CTA r
-    }
-    cluster.sync();
-    int g = kInf;
-    for (int r = 0; r < csize; ++r) g = min(g, s_mins[par][r]);
-    par ^= 1;
-    if (g == kInf) continue;                         // no 1 in this column at or below rpos (every CTA agrees)
-    bool const own_g = g >= p0 && g < p0 + kSlots, own_r = rpos >= p0 && rpos < p0 + kSlots;
-    if (own_g || own_r) {
+    for (int i = 0; i < kClThreads / 32; ++i) bm = min(bm, s_warp[i]);
+    bool const own_r = rpos >= p0 && rpos < p0 + kSlots;
+    if ((bm != kInf && mine == bm) || own_r || (bm == kInf && tid == 0)) {
       U128 vg{0ull, 0ull}, vr{0ull, 0ull};
 #pragma unroll
       for (int k = 0; k < kSlots; ++k) {
-        if (p0 + k == g) vg = w[k];
+        if (p0 + k == bm) vg = w[k];
         if (p0 + k == rpos) vr = w[k];
       }
       for (int r = 0; r < csize; ++r) {
-        if (own_g) {
-          unsigned long long *d = cluster.map_shared_rank(s_pw, r);
-          d[0] = vg.lo;
-          d[1] = vg.hi;
+        if (mine == bm || (bm == kInf && tid == 0)) {
+          Cand *d = cluster.map_shared_rank(&s_cand[par][crank], r);
+          d->lo = vg.lo;
+          d->hi = vg.hi;
+          d->pos = bm;
         }
         if (own_r) {
-          unsigned long long *d = cluster.map_shared_rank(s_rw, r);
+          unsigned long long *d = cluster.map_shared_rank(s_rw[par], r);
           d[0] = vr.lo;
           d[1] = vr.hi;
         }
       }
     }
     cluster.sync();
-    U128 const pw{s_pw[0], s_pw[1]}, rw{s_rw[0], s_rw[1]};
+    int g = kInf, gi = 0;
+    for (int r = 0; r < csize; ++r)
+      if (s_cand[par][r].pos < g) { g = s_cand[par][r].pos; gi = r; }
+    U128 const pw{s_cand[par][gi].lo, s_cand[par][gi].hi}, rw{s_rw[par][0], s_rw[par][1]};
+    par ^= 1;
+    if (g == kInf) continue;                         // no 1 in this column at or below rpos (every CTA agrees)
     U128 const m = above(j);
     unsigned long long const plo = pw.lo & m.lo, phi = pw.hi & m.hi;
 #pragma unroll
