@@ -255,6 +255,8 @@ def run_own_arm(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
+    if world > 1:   # all ranks stage pageable rows at the same time: share the host's threads instead of oversubscribing them
+        os.environ.setdefault("M4RI_B200_STAGE_THREADS", str(max(2, min(12, host_threads() // world - 1))))
     lib = m4ri_b200.load_library()
     if lib.m4ri_b200_device_count() < 1:
         raise SystemExit("no CUDA device: m4ri_b200 has no CPU fallback")
@@ -768,6 +770,60 @@ def run_own_arm(args):
         if not ok:
             raise SystemExit(3)
 
+    # ---- N > 1: the same product through the in-process C-ABI entry point (mzd_mul_mp / mzd_addmul_mp over all GPUs of
+    #      the box, csrc/multi.cu) on rank 0, with full pageable host matrices; the other ranks wait -----------------
+    inproc = None
+    if world > 1 and not args.no_inproc and not leaf_only:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        # the other ranks wait on the HOST (key in the rendezvous store): an NCCL barrier would park a kernel on their GPUs,
+        # which are about to be driven by rank 0
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            fullA = np.empty((m, l // 64), dtype=np.uint64)
+            fullB = np.empty((l, n // 64), dtype=np.uint64)
+            fullC = np.zeros((m, n // 64), dtype=np.uint64)
+            fullA[:, :] = H.seeded_words(H.SEED_A, m, l // 64)
+            fullB[:, :] = H.seeded_words(H.SEED_B, l, n // 64)
+            fA = make_header(MzdT, fullA.ctypes.data, m, l, l // 64)
+            fB = make_header(MzdT, fullB.ctypes.data, l, n, n // 64)
+            fC = make_header(MzdT, fullC.ctypes.data, m, n, n // 64)
+            mp_fn = lib.mzd_addmul_mp if accumulate else lib.mzd_mul_mp
+            lib.m4ri_b200_set_num_devices(world)
+
+            def reset_full_c():
+                if accumulate:
+                    fullC[:, :] = H.seeded_words(H.SEED_C, m, n // 64)
+
+            reset_full_c()
+            mp_fn(ctypes.byref(fC), ctypes.byref(fA), ctypes.byref(fB), cutoff)     # warm-up: contexts, workspaces, peer access
+            runs = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            for _ in range(runs):
+                mp_fn(ctypes.byref(fC), ctypes.byref(fA), ctypes.byref(fB), cutoff)
+            sec = (time.perf_counter() - t0) / runs
+            mp_path = lib.m4ri_b200_last_path().decode()
+            ok = None
+            gpath = os.path.join(ROOT, "tests", "golden", "large_golden.json")
+            if os.path.exists(gpath):
+                with open(gpath) as f:
+                    case = json.load(f)["cases"].get(golden_name)
+                if case and (case["m"], case["l"], case["n"]) == (m, l, n):
+                    reset_full_c()
+                    mp_fn(ctypes.byref(fC), ctypes.byref(fA), ctypes.byref(fB), cutoff)
+                    ok = H.large_block_digests(fullC) == case["C_blocks"]
+            lib.m4ri_b200_set_num_devices(1)
+            inproc = {"value": total_bitops / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "host_memory": "pageable",
+                      "h2d_bytes_per_step": (m * l + l * n + (m * n if accumulate else 0)) // 8, "d2h_bytes_per_step": m * n // 8,
+                      "api": ("mzd_addmul_mp" if accumulate else "mzd_mul_mp") + "(C, A, B, cutoff) on host mzd_t, one process driving "
+                             f"{world} GPUs (csrc/multi.cu)", "path": mp_path, "reference_digest": ok, "runs": runs}
+            del fullA, fullB, fullC
+            store.set("m4ri_b200_inproc_done", "1")
+        else:
+            import datetime
+            store.wait(["m4ri_b200_inproc_done"], datetime.timedelta(seconds=900))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -876,6 +932,8 @@ def run_own_arm(args):
         line["e2e"] = e2e[kinds[0]]
         for k in kinds[1:]:
             line["e2e_" + k] = e2e[k]
+    if inproc is not None:
+        line["e2e_inproc"] = inproc
     if verified is not None:
         line["verified"] = verified
     if add_roofline is not None:
@@ -908,6 +966,7 @@ def main():
                          "schedule needs them; 'kchunk' = K-chunk pipeline (m4ri_b200/shard.py); 'serial' = one after the other")
     ap.add_argument("--ksub", type=int, default=1, help="N > 1 end to end: sub-chunks per B row-slice (K-chunks = pr * ksub)")
     ap.add_argument("--chunk-levels", type=int, default=-1, help="N > 1 end to end: Strassen levels of a chunk product (-1: library rule)")
+    ap.add_argument("--no-inproc", action="store_true", help="N > 1: skip the in-process mzd_mul_mp leg on rank 0")
     ap.add_argument("--no-check", action="store_true", help="skip the verification after the timed legs")
     ap.add_argument("--verify", action="store_true", help="check this rank's C block against the oracle (small --size only)")
     args = ap.parse_args()

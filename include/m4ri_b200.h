@@ -20,6 +20,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -142,6 +143,16 @@ void   m4ri_b200_mzd_free(mzd_t *M);
  * mzd_init when one is loaded, else from m4ri_b200_mzd_init) */
 void   m4ri_b200_result_free(mzd_t *M);
 
+/* Interchange (m4ri/io.h; io.c:49-68, 297-357): same formats and semantics as mzd_from_str, mzd_from_jcf and
+ * mzd_fprint_row; to_jcf is the inverse of the reader (returns 2 for a matrix with an empty row, which JCF cannot
+ * express); PBM "P4" is the libpng-free 1-bit image interchange (the reference's PNG pair needs libpng). */
+mzd_t *m4ri_b200_from_str(rci_t m, rci_t n, char const *str);
+mzd_t *m4ri_b200_from_jcf(char const *fn, int verbose);
+int    m4ri_b200_to_jcf(mzd_t const *A, char const *fn);
+void   m4ri_b200_fprint_row(FILE *stream, mzd_t const *M, rci_t i);
+int    m4ri_b200_to_pbm(mzd_t const *A, char const *fn);
+mzd_t *m4ri_b200_from_pbm(char const *fn);
+
 /* Device-resident matrix: bit-packed rows exactly like mzd_t (64-bit words, LSB-first),
  * pitch a multiple of 2 words, base 16-byte aligned, and every bit between ncols and
  * the pitch zero. */
@@ -158,6 +169,7 @@ m4ri_b200_dmat *m4ri_b200_dmat_alloc(rci_t nrows, rci_t ncols);   /* zero-filled
  * even and >= ceil(ncols/128)*2, padding bits must be zero. */
 m4ri_b200_dmat *m4ri_b200_dmat_wrap(void *device_ptr, int64_t pitch_words, rci_t nrows, rci_t ncols);
 void            m4ri_b200_dmat_free(m4ri_b200_dmat *M);
+m4ri_b200_dmat *m4ri_b200_dmat_from_jcf(char const *fn, int verbose);   /* JCF file -> device-resident matrix (NULL on error) */
 /* host mzd_t (any window/stride/excess) -> device (excess bits cleared) and back (bits of
  * the host matrix outside nrows x ncols are preserved).  stream: cudaStream_t or NULL. */
 void m4ri_b200_upload(m4ri_b200_dmat *dst, mzd_t const *src, void *stream);

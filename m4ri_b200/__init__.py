@@ -115,6 +115,13 @@ def _declare(lib):
     lib.m4ri_b200_dmul_levels.argtypes = [DMatP, DMatP, DMatP, c_int, c_int, c_void_p]
     lib.m4ri_b200_dmul_quads.argtypes = [DMatP * 4, DMatP * 4, DMatP * 4, c_int, c_int, c_void_p, POINTER(Hooks)]
     lib.m4ri_b200_result_free.argtypes = [MzdP]
+    lib.m4ri_b200_from_str.argtypes, lib.m4ri_b200_from_str.restype = [c_int, c_int, c_char_p], MzdP
+    lib.m4ri_b200_from_jcf.argtypes, lib.m4ri_b200_from_jcf.restype = [c_char_p, c_int], MzdP
+    lib.m4ri_b200_to_jcf.argtypes, lib.m4ri_b200_to_jcf.restype = [MzdP, c_char_p], c_int
+    lib.m4ri_b200_to_pbm.argtypes, lib.m4ri_b200_to_pbm.restype = [MzdP, c_char_p], c_int
+    lib.m4ri_b200_from_pbm.argtypes, lib.m4ri_b200_from_pbm.restype = [c_char_p], MzdP
+    lib.m4ri_b200_fprint_row.argtypes = [c_void_p, MzdP, c_int]
+    lib.m4ri_b200_dmat_from_jcf.argtypes, lib.m4ri_b200_dmat_from_jcf.restype = [c_char_p, c_int], DMatP
     for name in ("mzd_ple", "_mzd_ple"):
         getattr(lib, name).argtypes, getattr(lib, name).restype = [MzdP, MzpP, MzpP, c_int], c_int
     lib.m4ri_b200_dple.argtypes, lib.m4ri_b200_dple.restype = [DMatP, POINTER(c_int), POINTER(c_int), c_void_p], c_int

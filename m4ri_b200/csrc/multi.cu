@@ -11,16 +11,20 @@
 // bench.py uses NCCL all-gathers).  There is no K-sharding of the result: XOR over K-chunks is accumulated
 // locally.
 //
-// Pipeline (same schedule as m4ri_b200/shard.py: pipelined_product): the K range is cut into pr * sub chunks,
-// chunk (g, j) = sub-chunk j of the row-slice of B that GPU (g, gc) uploads.  One host thread per GPU
-//   uploads its pieces in the order it will consume them (own slice first, then g = gr + 1, ... mod pr),
-//   pulls the peers' pieces as soon as their upload events exist,
-//   enqueues C (^)= A_chunk * B_chunk (Strassen-Winograd over the M4RM leaf) per chunk,
-//   and downloads the C block in two row parts, the first while the second is still being computed.
-// XOR-accumulation over K-chunks is exact in any order.
+// Pipeline (the in-process form of bench.py's "hooks" mode): every GPU runs the Strassen-Winograd schedule of its block
+// with the TOP level on four separately allocated quadrants per operand (strassen_mul_quads) and transfer hooks.  One
+// host thread per GPU; when its schedule first needs quadrant q of A (B) it
+//   uploads its 1/pc (1/pr) row share of that quadrant and announces it (event + flag),
+//   pulls the other shares from the GPUs of its row (column) group as soon as they are announced (copy engines),
+//   and makes the compute stream wait for exactly that quadrant;
+// result quadrants are downloaded as soon as they are final (three of the four before the last product starts).
+// A first version cut the K range into chunks instead (m4ri_b200/shard.py: pipelined_product, still an option of
+// bench.py); it overlapped as well but a chunk product is one Strassen level shallower than the whole block's:
+// 2 GPUs, 65536^3, pageable host matrices: 88 ms (K-chunks) against 74 ms for the quadrant hooks in bench.py.
 #include <string.h>
 
 #include <atomic>
+#include <functional>
 #include <memory>
 #include <thread>
 
@@ -31,7 +35,7 @@
 namespace m4b {
 namespace {
 
-constexpr int kTail = 2;          // row parts of the last chunk's product (download overlap)
+constexpr int kTail = 4;          // per-quadrant scratch for partial last words of a download
 
 struct Dev {
   int          id = 0;
@@ -100,14 +104,7 @@ struct Signal {
   }
 };
 
-int ksub_default() {
-  static int const v = [] {
-    char const *env = getenv("M4RI_B200_MP_KSUB");
-    int const k = env ? atoi(env) : 0;
-    return k >= 1 && k <= 16 ? k : 2;     // measured on 2 GPUs, pageable host matrices: 90.0 ms (1) vs 80.7 ms (2)
-  }();
-  return v;
-}
+int64_t gcd64(int64_t a, int64_t b) { return b ? gcd64(b, a % b) : a; }
 
 }  // namespace
 
@@ -141,47 +138,52 @@ void multi_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool cl
 
   int pr, pc;
   multi_grid(G, n, &pr, &pc);
-  int const sub = ksub_default(), S = pr * sub;
-  // geometry: row blocks of 64-row granules, column blocks and K-chunks of (128 << levels)-bit granules, so that
-  // every device view is 16-byte aligned and every Strassen level of a chunk product halves exactly
-  int const rb0 = (int)round_up64((m + pr - 1) / pr, 64), cb0 = (n + pc - 1) / pc, kc0 = imax((l + S - 1) / S, 1);
-  int const levels = l > 0 ? strassen_levels(imin(rb0, m), kc0, cb0, cutoff) : 0;
-  int const rb  = (int)round_up64(rb0, (int64_t)kTail * pc * (1 << levels));   // rows per block on the device
-  int const cb  = (int)round_up64(cb0, 128LL << levels);
-  int const kc  = (int)round_up64(kc0, 128LL << levels);
-  int const part = rb / pc;                                                    // A rows one GPU of a row group uploads
-  snprintf(path_out, path_len, levels ? "mp%d:%dx%d:k%d:strassen:%d" : "mp%d:%dx%d:k%d:m4rm", G, pr, pc, S, levels);
+  // geometry: every GPU multiplies (rb x lp) * (lp x cb) with at least one Strassen level, whose top level runs on four
+  // separately allocated quadrants per operand (strassen_mul_quads): a quadrant is the unit of upload, exchange and
+  // download.  Quadrant rows split into pc (A) resp. pr (B) equal shares, every quadrant halves `levels - 1` more times.
+  int const rb0 = (m + pr - 1) / pr, cb0 = (n + pc - 1) / pc;
+  int levels = l > 0 ? strassen_levels(rb0, l, cb0, cutoff) : 1;
+  if (levels < 1) levels = 1;
+  int64_t const sub = 1LL << (levels - 1);
+  int const rb = (int)round_up64(rb0, 2 * pc * sub * 64 / gcd64(2 * pc * sub, 64));      // multiple of 64 and of 2 * pc * sub
+  int const cb = (int)round_up64(cb0, 256 * sub);
+  int const lp = (int)round_up64(l > 0 ? l : 1, (int64_t)2 * pr * 128 * sub / gcd64(pr, sub) );   // >= multiple of 2*pr and 256*sub
+  int const m2 = rb / 2, k2 = lp / 2, n2 = cb / 2;
+  int const share_a = m2 / pc, share_b = k2 / pr;
+  snprintf(path_out, path_len, "mp%d:%dx%d:strassen:%d", G, pr, pc, levels);
 
-  // signals: A parts [producer device][chunk], B chunks [producer device][j]
-  std::vector<Signal> sigA((size_t)G * S), sigB((size_t)G * sub), sigZero(G);
+  // signals [producer GPU][quadrant]
+  std::vector<Signal> sigA((size_t)G * 4), sigB((size_t)G * 4), sigZero(G);
   auto make_event = [](Signal &s, int device) {
     M4B_CUDA(cudaSetDevice(device));
     M4B_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
   };
   for (int d = 0; d < G; ++d) {
-    for (int c = 0; c < S; ++c) make_event(sigA[(size_t)d * S + c], dev(d).id);
-    for (int j = 0; j < sub; ++j) make_event(sigB[(size_t)d * sub + j], dev(d).id);
+    for (int q = 0; q < 4; ++q) {
+      make_event(sigA[(size_t)d * 4 + q], dev(d).id);
+      make_event(sigB[(size_t)d * 4 + q], dev(d).id);
+    }
     make_event(sigZero[d], dev(d).id);
   }
 
   struct Bufs {
-    std::vector<DView> Ac, Bc;   // per chunk index c = g * sub + j
-    DView Cb;
+    DView a[4], b[4], c[4];
   };
   std::vector<Bufs> bufs(G);
   // buffers first (every thread needs its peers' addresses), then the pipelines
   for (int d = 0; d < G; ++d) {
     Dev &D = dev(d);
     M4B_CUDA(cudaSetDevice(D.id));
-    size_t need = Workspace::bytes_for(rb, cb) + strassen_workspace_bytes(rb, kc, cb, levels);
-    need += (size_t)S * (Workspace::bytes_for(rb, kc) + Workspace::bytes_for(kc, cb));
+    size_t const need = 4 * (Workspace::bytes_for(m2, k2) + Workspace::bytes_for(k2, n2) + Workspace::bytes_for(m2, n2)) +
+                        strassen_workspace_bytes(rb, lp, cb, levels) + 3 * Workspace::bytes_for(m2 > k2 ? m2 : k2, k2 > n2 ? k2 : n2);
     D.ws.reserve(need);
     Bufs &b = bufs[d];
-    b.Ac.resize(S);
-    b.Bc.resize(S);
-    for (int c = 0; c < S; ++c) b.Ac[c] = D.ws.alloc(rb, kc);
-    for (int c = 0; c < S; ++c) b.Bc[c] = D.ws.alloc(kc, cb);
-    b.Cb = D.ws.alloc(rb, cb);
+    for (int q = 0; q < 4; ++q) b.a[q] = D.ws.alloc(m2, k2);
+    for (int q = 0; q < 4; ++q) b.b[q] = D.ws.alloc(k2, n2);
+    for (int q = 0; q < 4; ++q) b.c[q] = D.ws.alloc(m2, n2);
+    // a fixed share of the host's copy threads per GPU (all GPUs stage pageable rows at the same time)
+    int const hw = (int)std::thread::hardware_concurrency();
+    D.stager.set_threads(hw / G < 2 ? 2 : hw / G);
   }
 
   std::vector<std::thread> threads;
@@ -191,104 +193,142 @@ void multi_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool cl
       M4B_CUDA(cudaSetDevice(D.id));
       Bufs &b = bufs[d];
       int const gr = d / pc, gc = d % pc;
-      int const r0 = imin(gr * rb0, m), r1 = imin((gr + 1) * rb0, m);     // host rows of this block
+      int const r0 = imin(gr * rb, m), r1 = imin((gr + 1) * rb, m);       // host rows of this block
       int const c0 = imin(gc * cb, n), c1 = imin((gc + 1) * cb, n);       // host columns of this block
       bool const has_c = r1 > r0 && c1 > c0;
 
       // padding must read as zeros: clear everything once, uploads and peer copies are ordered after it
-      for (int c = 0; c < S; ++c) {
-        zero_async(b.Ac[c], D.compute);
-        zero_async(b.Bc[c], D.compute);
+      for (int q = 0; q < 4; ++q) {
+        zero_async(b.a[q], D.compute);
+        zero_async(b.b[q], D.compute);
+        if (!clear) zero_async(b.c[q], D.compute);
       }
-      if (!clear) zero_async(b.Cb, D.compute);
       sigZero[d].post(D.compute);
       M4B_CUDA(cudaStreamWaitEvent(D.up, sigZero[d].ev, 0));
       M4B_CUDA(cudaStreamWaitEvent(D.xfer, sigZero[d].ev, 0));
 
-      cudaEvent_t evC = nullptr, evTail[kTail] = {};
-      if (!clear && has_c) {
-        mzd_t Cw = host_window(C, r0, c0, r1, c1);
-        upload(b.Cb.sub(0, 0, Cw.nrows, cb), &Cw, D.up, &D.stager);
-        M4B_CUDA(cudaEventCreateWithFlags(&evC, cudaEventDisableTiming));
-        M4B_CUDA(cudaEventRecord(evC, D.up));
-      }
-      std::vector<cudaEvent_t> evReady(S, nullptr);
+      // Transfer hooks of the top Strassen level: a quadrant is uploaded (this GPU's share), announced, completed from
+      // the peers of the row / column group over NVLink, and the compute stream waits for exactly that.
+      struct Hooks : TopHooks {
+        std::function<void(int)> fa, fb, fc, fd;
+        void need_a(int q) override { fa(q); }
+        void need_b(int q) override { fb(q); }
+        void need_c(int q) override { fc(q); }
+        void done_c(int q) override { fd(q); }
+      } hk;
+      bool upA[4] = {}, upB[4] = {}, upC[4] = {};
+      std::vector<cudaEvent_t> events;
+      auto event = [&] {
+        cudaEvent_t e;
+        M4B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        events.push_back(e);
+        return e;
+      };
+      auto post_a = [&](int q) {          // upload this GPU's row share of A quadrant q and announce it
+        if (upA[q]) return;
+        upA[q] = true;
+        int const hr0 = r0 + (q >> 1) * m2 + gc * share_a, hc0 = (q & 1) * k2;
+        if (hr0 < r1 && hc0 < l) {
+          mzd_t W = host_window(A, hr0, hc0, imin(hr0 + share_a, imin(r0 + ((q >> 1) + 1) * m2, r1)), hc0 + k2);
+          if (W.nrows > 0 && W.ncols > 0) upload(b.a[q].sub(gc * share_a, 0, gc * share_a + W.nrows, k2), &W, D.up, &D.stager);
+        }
+        sigA[(size_t)d * 4 + q].post(D.up);
+      };
+      auto post_b = [&](int q) {          // this GPU's row share of quadrant q of B[:, cols gc]
+        if (upB[q]) return;
+        upB[q] = true;
+        int const hr0 = (q >> 1) * k2 + gr * share_b, hc0 = c0 + (q & 1) * n2;
+        if (hr0 < l && hc0 < c1) {
+          mzd_t W = host_window(B, hr0, hc0, imin(hr0 + share_b, l), imin(hc0 + n2, c1));
+          if (W.nrows > 0 && W.ncols > 0) upload(b.b[q].sub(gr * share_b, 0, gr * share_b + W.nrows, n2), &W, D.up, &D.stager);
+        }
+        sigB[(size_t)d * 4 + q].post(D.up);
+      };
+      hk.fa = [&](int q) {
+        bool const first = !upA[q];
+        post_a(q);
+        if (!first) return;
+        for (int p = 0; p < pc; ++p) {
+          int const peer = gr * pc + p;
+          if (p == gc) {
+            M4B_CUDA(cudaStreamWaitEvent(D.xfer, sigA[(size_t)d * 4 + q].ev, 0));
+            continue;
+          }
+          sigA[(size_t)peer * 4 + q].await_on(D.xfer);
+          size_t const off = (size_t)p * share_a * (size_t)b.a[q].pitch;
+          M4B_CUDA(cudaMemcpyPeerAsync(b.a[q].data + off, D.id, bufs[peer].a[q].data + off, dev(peer).id,
+                                       (size_t)share_a * (size_t)b.a[q].pitch * 8, D.xfer));
+        }
+        cudaEvent_t e = event();
+        M4B_CUDA(cudaEventRecord(e, D.xfer));
+        M4B_CUDA(cudaStreamWaitEvent(D.compute, e, 0));
+      };
+      hk.fb = [&](int q) {
+        bool const first = !upB[q];
+        post_b(q);
+        if (!first) return;
+        for (int p = 0; p < pr; ++p) {
+          int const peer = p * pc + gc;
+          if (p == gr) {
+            M4B_CUDA(cudaStreamWaitEvent(D.xfer, sigB[(size_t)d * 4 + q].ev, 0));
+            continue;
+          }
+          sigB[(size_t)peer * 4 + q].await_on(D.xfer);
+          size_t const off = (size_t)p * share_b * (size_t)b.b[q].pitch;
+          M4B_CUDA(cudaMemcpyPeerAsync(b.b[q].data + off, D.id, bufs[peer].b[q].data + off, dev(peer).id,
+                                       (size_t)share_b * (size_t)b.b[q].pitch * 8, D.xfer));
+        }
+        cudaEvent_t e = event();
+        M4B_CUDA(cudaEventRecord(e, D.xfer));
+        M4B_CUDA(cudaStreamWaitEvent(D.compute, e, 0));
+      };
+      auto c_window = [&](int q) {
+        int const hr0 = r0 + (q >> 1) * m2, hc0 = c0 + (q & 1) * n2;
+        if (hr0 >= r1 || hc0 >= c1) {
+          mzd_t W = *C;
+          W.nrows = W.ncols = 0;
+          return W;
+        }
+        return host_window(C, hr0, hc0, imin(hr0 + m2, r1), imin(hc0 + n2, c1));
+      };
+      hk.fc = [&](int q) {
+        if (upC[q]) return;
+        upC[q] = true;
+        mzd_t W = c_window(q);
+        if (W.nrows > 0 && W.ncols > 0) upload(b.c[q].sub(0, 0, W.nrows, n2), &W, D.up, &D.stager);
+        cudaEvent_t e = event();
+        M4B_CUDA(cudaEventRecord(e, D.up));
+        M4B_CUDA(cudaStreamWaitEvent(D.compute, e, 0));
+      };
+      cudaEvent_t ready[4] = {};
+      int order[4], ndone = 0;
+      hk.fd = [&](int q) {
+        ready[q] = event();
+        M4B_CUDA(cudaEventRecord(ready[q], D.compute));
+        order[ndone++] = q;
+      };
 
-      // schedule: own slice first, then the others in rotated order
-      for (int idx = 0; idx < S; ++idx) {
-        int const g = (gr + idx / sub) % pr, j = idx % sub, c = g * sub + j;
-        int const k0 = c * kc;                                            // host columns of A / rows of B
-        bool const own = g == gr;
-        // ---- uploads of this position --------------------------------------------------------------
-        if (own) {      // B sub-chunk j of the slice this GPU contributes to its column group
-          if (k0 < l && c1 > c0) {
-            mzd_t Bw = host_window(B, k0, c0, k0 + kc, c1);
-            if (Bw.nrows > 0) upload(b.Bc[c].sub(0, 0, Bw.nrows, cb), &Bw, D.up, &D.stager);
-          }
-          sigB[(size_t)d * sub + j].post(D.up);
-        }
-        {               // this GPU's row part of A chunk c (it serves the whole row group)
-          int const pr0 = r0 + gc * part, pr1 = imin(pr0 + part, r1);
-          if (pr1 > pr0 && k0 < l) {
-            mzd_t Aw = host_window(A, pr0, k0, pr1, k0 + kc);
-            if (Aw.ncols > 0) upload(b.Ac[c].sub(gc * part, 0, gc * part + Aw.nrows, kc), &Aw, D.up, &D.stager);
-          }
-          sigA[(size_t)d * S + c].post(D.up);
-        }
-        // ---- pull the peers' pieces over NVLink (copy engines) -----------------------------------------
-        if (has_c) {
-          for (int q = 0; q < pc; ++q) {
-            int const p = gr * pc + q;
-            if (q == gc) {
-              M4B_CUDA(cudaStreamWaitEvent(D.xfer, sigA[(size_t)d * S + c].ev, 0));
-              continue;
-            }
-            sigA[(size_t)p * S + c].await_on(D.xfer);
-            size_t const off = (size_t)q * part * (size_t)b.Ac[c].pitch;
-            M4B_CUDA(cudaMemcpyPeerAsync(b.Ac[c].data + off, D.id, bufs[p].Ac[c].data + off, dev(p).id,
-                                         (size_t)part * (size_t)b.Ac[c].pitch * 8, D.xfer));
-          }
-          int const pb = g * pc + gc;                                     // producer of B chunk (g, j) in this column group
-          if (pb == d) {
-            M4B_CUDA(cudaStreamWaitEvent(D.xfer, sigB[(size_t)d * sub + j].ev, 0));
-          } else {
-            sigB[(size_t)pb * sub + j].await_on(D.xfer);
-            M4B_CUDA(cudaMemcpyPeerAsync(b.Bc[c].data, D.id, bufs[pb].Bc[c].data, dev(pb).id,
-                                         (size_t)kc * (size_t)b.Bc[c].pitch * 8, D.xfer));
-          }
-          M4B_CUDA(cudaEventCreateWithFlags(&evReady[c], cudaEventDisableTiming));
-          M4B_CUDA(cudaEventRecord(evReady[c], D.xfer));
-          // ---- the product of this chunk ----------------------------------------------------------------
-          M4B_CUDA(cudaStreamWaitEvent(D.compute, evReady[c], 0));
-          if (evC) M4B_CUDA(cudaStreamWaitEvent(D.compute, evC, 0));
-          bool const clr = clear && idx == 0;
-          if (idx + 1 < S) {
-            strassen_mul(b.Cb, b.Ac[c], b.Bc[c], levels, clr, D.ws, D.compute);
-          } else {
-            for (int t = 0; t < kTail; ++t) {
-              int const t0 = t * (rb / kTail), t1 = (t + 1) * (rb / kTail);
-              strassen_mul(b.Cb.sub(t0, 0, t1, cb), b.Ac[c].sub(t0, 0, t1, kc), b.Bc[c], levels, clr, D.ws, D.compute);
-              M4B_CUDA(cudaEventCreateWithFlags(&evTail[t], cudaEventDisableTiming));
-              M4B_CUDA(cudaEventRecord(evTail[t], D.compute));
-            }
-          }
-        }
-      }
-      // ---- downloads, issued after every product has been enqueued (a D2H copy blocks this thread) ---------
-      mzd_t parts[kTail];
       if (has_c) {
-        for (int t = 0; t < kTail; ++t) {
-          int const t0 = t * (rb / kTail), t1 = (t + 1) * (rb / kTail);
-          parts[t] = host_window(C, r0 + t0, c0, imin(r0 + t1, r1), c1);
-          M4B_CUDA(cudaStreamWaitEvent(D.down, evTail[t], 0));
-          if (parts[t].nrows > 0)
-            download(&parts[t], b.Cb.sub(t0, 0, t0 + parts[t].nrows, cb), D.down, D.tmp[t], &D.stager);
+        strassen_mul_quads(b.c, b.a, b.b, levels, clear, D.ws, D.compute, hk);
+        // downloads, issued after the whole schedule has been enqueued (a D2H copy blocks this thread)
+        mzd_t win[4];
+        for (int i = 0; i < ndone; ++i) {
+          int const q = order[i];
+          win[q] = c_window(q);
+          M4B_CUDA(cudaStreamWaitEvent(D.down, ready[q], 0));
+          if (win[q].nrows > 0 && win[q].ncols > 0)
+            download(&win[q], b.c[q].sub(0, 0, win[q].nrows, n2), D.down, D.tmp[q], &D.stager);
+        }
+      } else {
+        // nothing to compute here, but the peers still need this GPU's shares (in the order their schedules ask for them)
+        static int const kOrderA[4] = {1, 3, 2, 0}, kOrderB[4] = {2, 3, 1, 0};
+        for (int i = 0; i < 4; ++i) {
+          post_b(kOrderB[i]);
+          post_a(kOrderA[i]);
         }
       }
       for (cudaStream_t s : {D.down, D.compute, D.xfer, D.up}) M4B_CUDA(cudaStreamSynchronize(s));
-      if (evC) cudaEventDestroy(evC);
-      for (cudaEvent_t e : evTail) if (e) cudaEventDestroy(e);
-      for (cudaEvent_t e : evReady) if (e) cudaEventDestroy(e);
+      for (cudaEvent_t e : events) cudaEventDestroy(e);
     });
   }
   for (auto &t : threads) t.join();

@@ -21,6 +21,7 @@ void Stager::ensure() {
   // 12: 111.2 ms (pinned: 107.3 ms) — default = the host's threads minus four, between 4 and 12
   int const hw = (int)std::thread::hardware_concurrency();
   kThreads = hw - 4 < 4 ? 4 : (hw - 4 > 12 ? 12 : hw - 4);
+  if (forced_threads_ > 0) kThreads = forced_threads_ > kMaxThreads ? kMaxThreads : forced_threads_;
   if (char const *env = getenv("M4RI_B200_STAGE_THREADS")) {
     int const t = atoi(env);
     if (t >= 1 && t <= kMaxThreads) kThreads = t;
@@ -32,6 +33,15 @@ void Stager::ensure() {
   stop_ = false;
   for (int t = 1; t < kThreads; ++t) threads_.emplace_back([this, t] { worker(t); });
   ready_ = true;
+}
+
+void Stager::set_threads(int n) {
+  if (n == forced_threads_) return;
+  forced_threads_ = n;
+  if (ready_) {                      // restart the ring with the new thread count at its next use
+    for (int i = 0; i < kSlots; ++i) cudaEventSynchronize(done_[i]);
+    release();
+  }
 }
 
 void Stager::release() {

@@ -33,12 +33,14 @@ class Stager {
   void download2d(void *dst, size_t dpitch, void const *src, size_t spitch, size_t width, size_t rows, cudaStream_t s);
 
   void release();   // free pinned memory, stop the threads
+  void set_threads(int n);   // copy threads incl. the caller (takes effect at the next start of the ring)
 
  private:
   static constexpr size_t kChunkBytes = 8u << 20;
   static constexpr int    kSlots = 4;
   static constexpr int    kMaxThreads = 16;
   int kThreads = 4;                 // copy threads incl. the caller ($M4RI_B200_STAGE_THREADS, read once in ensure())
+  int forced_threads_ = 0;
 
   void ensure();
   void parallel_rows(size_t rows, std::function<void(size_t, size_t)> const &fn);
