@@ -658,6 +658,7 @@ def run_own_arm(args):
     leaf_ms, leaf_bitops = ctypes.c_double(0), ctypes.c_double(0)
     leaf_launches = lib.m4ri_b200_profile_end(ctypes.byref(leaf_ms), ctypes.byref(leaf_bitops))
     launches = lib.m4ri_b200_kernel_launches() - launches0
+    leaf_variant = lib.m4ri_b200_last_leaf_variant()      # of the timed region (later legs launch other leaves)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_step = max_over_ranks(total_ms / args.steps)
     path = lib.m4ri_b200_last_path().decode()
@@ -839,7 +840,6 @@ def run_own_arm(args):
     # The tall-tile leaf (variant 2, m4rm_leaf2.cu) per step of 32 A-columns on a 4096 x 256-bit tile: 4096 rows x 8
     # 16-byte lookups + 2048 16-byte table pieces written + A (4096 x 4 B) and B (32 x 32 B) = 574464 B per
     # 2*32*4096*256 bit-ops.
-    leaf_variant = lib.m4ri_b200_last_leaf_variant()
     if leaf_variant == 2:
         smem_bytes_per_bitop = (4096 * 8 * 16 + 2048 * 16 + 4096 * 4 + 32 * 32) / (2.0 * 32 * 4096 * 256)
         lookup_bytes_per_bitop = (4096 * 8 * 16) / (2.0 * 32 * 4096 * 256)

@@ -60,13 +60,43 @@ L2_FN void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// L2 residency hints (round 2): a launch of 49 products touches ~300 MB — the A panels (2 MiB each, re-read by every
+// column tile of their product) compete with the B and C streams for the 126 MB L2, and ncu showed 2.3 GB of DRAM
+// traffic per launch against 0.4 GB of algorithmic bytes.  A is loaded evict_last, B evict_first.
+__constant__ int g_l2hint = 1;
+
+L2_FN unsigned long long policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+L2_FN unsigned long long policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
 L2_FN void tma_load_2d(uint32_t dst, TMap const *map, int c0, int c1, uint32_t bar) {
+  if (g_l2hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy_evict_last())
+        : "memory");
+    return;
+  }
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
 L2_FN void tma_load_3d(uint32_t dst, TMap const *map, int c0, int c1, int c2, uint32_t bar) {
+  if (g_l2hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy_evict_last())
+        : "memory");
+    return;
+  }
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
@@ -74,6 +104,12 @@ L2_FN void tma_load_3d(uint32_t dst, TMap const *map, int c0, int c1, int c2, ui
 }
 // LDGSTS: 16 bytes global -> shared without a register round trip; src_bytes = 0 writes zeros
 L2_FN void cp_async16(uint32_t dst, void const *src, uint32_t src_bytes) {
+  if (g_l2hint) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes),
+                 "l"(policy_evict_first())
+                 : "memory");
+    return;
+  }
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 L2_FN void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
@@ -136,6 +172,10 @@ void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *
     if (s && (s[0] == '0' || s[0] == '1')) return s[0] == '1' ? 2 : 0;
     return kDefaultSplit ? 2 : 0;
   }();
+  static int const l2hint = [] {
+    char const *e = getenv("M4RI_B200_LEAF2_L2HINT");
+    return e && e[0] == '0' ? 0 : 1;
+  }();
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
   auto kern = variant == 1 ? m4rm_leaf2_kernel<kThreads, 1, 0>
             : variant == 2 ? m4rm_leaf2_kernel<kThreads, 0, 1> : m4rm_leaf2_kernel<kThreads, 0, 0>;
@@ -143,6 +183,7 @@ void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *
   M4B_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
     M4B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    M4B_CUDA(cudaMemcpyToSymbol(leaf2::g_l2hint, &l2hint, sizeof l2hint));
     configured[dev & 63] = true;
   }
   if (count > kMaxBatch) die("m4ri_b200: batch of %d leaf products exceeds %d\n", count, kMaxBatch);
