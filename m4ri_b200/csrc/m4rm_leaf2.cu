@@ -63,7 +63,9 @@ L2_FN void mbar_wait(uint32_t bar, uint32_t parity) {
 // L2 residency hints (round 2): a launch of 49 products touches ~300 MB — the A panels (2 MiB each, re-read by every
 // column tile of their product) compete with the B and C streams for the 126 MB L2, and ncu showed 2.3 GB of DRAM
 // traffic per launch against 0.4 GB of algorithmic bytes.  A is loaded evict_last, B evict_first.
-__constant__ int g_l2hint = 1;
+// g_l2hint bits: 1 = A by TMA with an evict_last policy from createpolicy, 2 = B by cp.async with an evict_first policy,
+// 4 = A by TMA with the fixed evict_last descriptor CUTLASS uses (0x14F0000000000000).  $M4RI_B200_LEAF2_L2HINT.
+__constant__ int g_l2hint = 0;
 
 L2_FN unsigned long long policy_evict_last() {
   unsigned long long p;
@@ -77,10 +79,11 @@ L2_FN unsigned long long policy_evict_first() {
 }
 
 L2_FN void tma_load_2d(uint32_t dst, TMap const *map, int c0, int c1, uint32_t bar) {
-  if (g_l2hint) {
+  if (g_l2hint & 5) {
+    unsigned long long const pol = (g_l2hint & 4) ? 0x14F0000000000000ull : policy_evict_last();
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy_evict_last())
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(pol)
         : "memory");
     return;
   }
@@ -90,10 +93,11 @@ L2_FN void tma_load_2d(uint32_t dst, TMap const *map, int c0, int c1, uint32_t b
       : "memory");
 }
 L2_FN void tma_load_3d(uint32_t dst, TMap const *map, int c0, int c1, int c2, uint32_t bar) {
-  if (g_l2hint) {
+  if (g_l2hint & 5) {
+    unsigned long long const pol = (g_l2hint & 4) ? 0x14F0000000000000ull : policy_evict_last();
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy_evict_last())
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(pol)
         : "memory");
     return;
   }
@@ -104,7 +108,7 @@ L2_FN void tma_load_3d(uint32_t dst, TMap const *map, int c0, int c1, int c2, ui
 }
 // LDGSTS: 16 bytes global -> shared without a register round trip; src_bytes = 0 writes zeros
 L2_FN void cp_async16(uint32_t dst, void const *src, uint32_t src_bytes) {
-  if (g_l2hint) {
+  if (g_l2hint & 2) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes),
                  "l"(policy_evict_first())
                  : "memory");
@@ -174,7 +178,7 @@ void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *
   }();
   static int const l2hint = [] {
     char const *e = getenv("M4RI_B200_LEAF2_L2HINT");
-    return e && e[0] == '0' ? 0 : 1;
+    return e ? atoi(e) & 7 : 0;
   }();
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
   auto kern = variant == 1 ? m4rm_leaf2_kernel<kThreads, 1, 0>
@@ -211,6 +215,12 @@ void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *
   }
   long long grid = m4rm_num_sms();
   if (grid > p.total_units) grid = p.total_units;
+  static int const hybrid = [] {       // M4RI_B200_LEAF2_HYBRID=0: pure stream-K over all units (the round-1 partition)
+    char const *e = getenv("M4RI_B200_LEAF2_HYBRID");
+    return e && e[0] == '0' ? 0 : 1;
+  }();
+  long long const tiles_total = (long long)p.tiles_m * p.tiles_n * count;
+  p.dp_rounds = hybrid ? (int)(tiles_total / grid) : 0;
   kern<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(p);
   M4B_CUDA(cudaGetLastError());
   ++g_kernel_launches;

@@ -252,6 +252,12 @@ bool run_case(int count, int m, int l, int n, int nblocks) {
     p.pitchB[i] = B[i].pitch;
   }
   if (nblocks > p.total_units) nblocks = (int)p.total_units;
+  // the launcher's hybrid partition: whole tiles round-robin first, stream-K over the rest (EMU_HYBRID=0: pure stream-K)
+  {
+    char const *e = getenv("EMU_HYBRID");
+    long long const tiles_total = (long long)p.tiles_m * p.tiles_n * count;
+    p.dp_rounds = (e && e[0] == '0') ? 0 : (int)(tiles_total / nblocks);
+  }
   g_bar_base = kEmuSbase + kOffBar;
 
   std::vector<std::thread> th;

@@ -25,6 +25,20 @@ def test_builtin_cases_bit_exact(emu):
     assert "FAIL" not in out.stdout and out.stdout.count("ok  ") >= 10, out.stdout
 
 
+@pytest.mark.parametrize("hybrid", ["0", "1"])
+@pytest.mark.parametrize("count,m,l,n,blocks", [
+    (3, 4096, 384, 1024, 5),         # 12 tiles on 5 CTAs: two whole-tile rounds + a stream-K tail of 2 tiles
+    (7, 4096, 256, 512, 4),          # 14 tiles on 4 CTAs: three rounds + tail
+    (1, 8192, 256, 768, 6),          # 6 tiles on 6 CTAs: one round, empty tail
+    (2, 5000, 300, 300, 3),          # ragged rows/columns, 8 tiles on 3 CTAs
+])
+def test_hybrid_partition(emu, hybrid, count, m, l, n, blocks):
+    """whole tiles round-robin first, stream-K over the rest (the launcher's default) and pure stream-K give the same bits"""
+    out = subprocess.run([emu, str(count), str(m), str(l), str(n), str(blocks)], capture_output=True, text=True,
+                         timeout=600, env=dict(os.environ, EMU_HYBRID=hybrid))
+    assert out.returncode == 0 and "FAIL" not in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.parametrize("count,m,l,n,blocks", [
     (1, 1, 1, 1, 1),                 # the smallest product
     (1, 4097, 129, 257, 2),          # one past every tile / slab / word edge
