@@ -73,6 +73,10 @@ void launch_winograd_post(DView const p[7], DView const c[4], bool accumulate, c
 void launch_winograd_pre_a_batch(int nodes, DView const *a, DView const *s_out, cudaStream_t stream);
 void launch_winograd_pre_b_batch(int nodes, DView const *b, DView const *t_out, cudaStream_t stream);
 void launch_winograd_post_batch(int nodes, DView const *p, DView const *c, cudaStream_t stream);
+// two Winograd levels in one pass (elementwise.cu): side 0 = A, 1 = B; sub[4*q1+q2] = quadrant q2 of quadrant q1;
+// sums[0..16) = level-1 sums by sub-block, sums[16+4*i+t] = level-2 sum t of level-1 operand i; prods[7*i+j]; csub[4*Q1+Q2]
+void launch_winograd_pre2(int side, DView const *sub, DView const *sums, cudaStream_t stream);
+void launch_winograd_post2(DView const *prods, DView const *csub, bool accumulate, cudaStream_t stream);
 
 // ---- host <-> device transfers (capi.cu) ----------------------------------------------
 class Stager;   // staging.h: pinned-ring transfers for pageable host memory (optional)

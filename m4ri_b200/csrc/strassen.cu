@@ -120,6 +120,7 @@ static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Wor
 // (every CTA of the stream-K partition ends with its red.xor merge at the same moment), which is 12 % of a
 // 7 x 4096^3 launch but 2 % of a 49 x 4096^3 one — this is what makes one more Strassen level pay.
 static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws, cudaStream_t s) {
+  static bool const fused = getenv("M4RI_B200_NO_FUSED2") == nullptr;   // the two-pass form, kept for A/B measurements
   DView a[4], b[4], c[4];
   quadrants(A, a);
   quadrants(B, b);
@@ -130,23 +131,38 @@ static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws,
   DView S[4], T[4], P1[7];
   for (int i = 0; i < 4; ++i) S[i] = ws.alloc(m2, k2);
   for (int i = 0; i < 4; ++i) T[i] = ws.alloc(k2, n2);
-  DView const P1all = ws.alloc(7 * m2, n2);
-  for (int i = 0; i < 7; ++i) P1[i] = P1all.sub(i * m2, 0, (i + 1) * m2, n2);
-  launch_winograd_pre_a(a, S, s);
-  launch_winograd_pre_b(b, T, s);
   DView const X1[7] = {a[0], a[1], S[3], a[3], S[0], S[1], S[2]};
   DView const Y1[7] = {b[0], b[2], b[3], T[3], T[0], T[1], T[2]};
   // ---- level 2 operands of all seven inner nodes ----
-  DView xa[28], xs[28], yb[28], yt[28], pq[28];
+  DView xa[28], xs[28], yb[28], yt[28];
   for (int i = 0; i < 7; ++i) {
     quadrants(X1[i], xa + 4 * i);
     quadrants(Y1[i], yb + 4 * i);
-    quadrants(P1[i], pq + 4 * i);
     for (int q = 0; q < 4; ++q) xs[4 * i + q] = ws.alloc(m4, k4);
     for (int q = 0; q < 4; ++q) yt[4 * i + q] = ws.alloc(k4, n4);
   }
-  launch_winograd_pre_a_batch(7, xa, xs, s);
-  launch_winograd_pre_b_batch(7, yb, yt, s);
+  if (fused) {
+    // both levels of operand sums in ONE pass per side: 16 sub-blocks in, the 4 level-1 sums (16 sub-blocks) and the
+    // 28 level-2 sums out
+    DView asub[16], bsub[16], asum[44], bsum[44];
+    for (int q1 = 0; q1 < 4; ++q1) {
+      quadrants(a[q1], asub + 4 * q1);
+      quadrants(b[q1], bsub + 4 * q1);
+      quadrants(S[q1], asum + 4 * q1);
+      quadrants(T[q1], bsum + 4 * q1);
+    }
+    for (int k = 0; k < 28; ++k) {
+      asum[16 + k] = xs[k];
+      bsum[16 + k] = yt[k];
+    }
+    launch_winograd_pre2(0, asub, asum, s);
+    launch_winograd_pre2(1, bsub, bsum, s);
+  } else {
+    launch_winograd_pre_a(a, S, s);
+    launch_winograd_pre_b(b, T, s);
+    launch_winograd_pre_a_batch(7, xa, xs, s);
+    launch_winograd_pre_b_batch(7, yb, yt, s);
+  }
   DView const P2all = ws.alloc(49 * m4, n4);
   DView P2[49], X2[49], Y2[49];
   for (int i = 0; i < 7; ++i) {
@@ -161,8 +177,20 @@ static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws,
   }
   launch_zero(P2all, s);
   launch_m4rm_batch(49, P2, X2, Y2, s);
-  launch_winograd_post_batch(7, P2, pq, s);          // P1[i] from its seven products, all i in one launch
-  launch_winograd_post(P1, c, !clear, s);
+  if (fused) {
+    DView csub[16];                                  // the 49 products straight into the 16 sub-blocks of C
+    for (int q1 = 0; q1 < 4; ++q1) quadrants(c[q1], csub + 4 * q1);
+    launch_winograd_post2(P2, csub, !clear, s);
+  } else {
+    DView const P1all = ws.alloc(7 * m2, n2);
+    DView pq[28];
+    for (int i = 0; i < 7; ++i) {
+      P1[i] = P1all.sub(i * m2, 0, (i + 1) * m2, n2);
+      quadrants(P1[i], pq + 4 * i);
+    }
+    launch_winograd_post_batch(7, P2, pq, s);          // P1[i] from its seven products, all i in one launch
+    launch_winograd_post(P1, c, !clear, s);
+  }
   ws.release(mark);
 }
 
