@@ -31,6 +31,11 @@ void Stager::ensure() {
     M4B_CUDA(cudaEventCreateWithFlags(&done_[i], cudaEventDisableTiming));
   }
   stop_ = false;
+  // no worker is alive here: restart the job counter they compare against (a worker of a re-created ring starts at
+  // generation 0 and would otherwise take the stale job pointer of the ring that was released)
+  generation_ = 0;
+  pending_ = 0;
+  job_ = nullptr;
   for (int t = 1; t < kThreads; ++t) threads_.emplace_back([this, t] { worker(t); });
   ready_ = true;
 }

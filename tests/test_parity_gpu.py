@@ -442,3 +442,19 @@ def test_entry_points_from_four_host_threads(lib):
     assert not errors, errors
     for job in jobs:
         H.free(*job)
+
+
+def test_staging_ring_survives_release(lib):
+    """m4ri_b200_release() frees the pinned staging ring and stops its copy threads; the next large pageable operand
+    must start a fresh ring (a re-created worker once picked up the stale job of the released ring)."""
+    m, l, n = 3000, 9000, 5000          # A: 3.4 MB, B: 5.6 MB > the 4 MiB staging threshold
+    A, B = H.new(m, l), H.new(l, n)
+    _fill_fast(A, 5); _fill_fast(B, 6)
+    want = H.oracle().orc_mul(None, A, B, 0)
+    for _ in range(3):
+        C = H.new(m, n)
+        lib.mzd_mul(C, A, B, 0)
+        assert np.array_equal(H.storage(C), H.storage(want))
+        H.free(C)
+        lib.m4ri_b200_release()
+    H.free(A, B, want)
