@@ -45,13 +45,16 @@ void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream);
 // products of identical shape in ONE persistent launch: 7 (the last Strassen level) with either leaf, up to 49
 // (the last TWO levels) where the tall-tile leaf suits — m4rm_batch_limit() says which
 void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream);
+// the same as C = A*B: C need not be initialised (the tall-tile leaf stores the tiles a CTA owns alone and zero-fills
+// only the products that hold stream-K tail tiles; the 1024-row leaf zero-fills everything first)
+void launch_m4rm_batch_clear(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream);
 int  m4rm_batch_limit(int m, int l, int n);
 // C = A*B for l <= 128 with plain stores; C may alias A or B
 void launch_m4rm_overwrite(DView C, DView A, DView B, cudaStream_t stream);
 int  m4rm_num_sms();
 // tall-tile leaf (m4rm_leaf2.cu): 4096 x 256-bit C tiles; worth it only when (nearly) all 4096 rows are real
 bool leaf2_suits(int m, int l, int n);
-void launch_m4rm_leaf2(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream);
+void launch_m4rm_leaf2(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream, bool overwrite = false);
 // 0 = automatic (leaf2 where it suits), 1 = always the 1024-row leaf, 2 = leaf2 whenever m >= 1
 extern int g_leaf_variant;
 extern int g_last_leaf;

@@ -477,7 +477,8 @@ static bool tall_leaf(int m, int l, int n, bool overwrite) {
 
 int m4rm_batch_limit(int m, int l, int n) { return tall_leaf(m, l, n, false) ? 49 : kMaxBatch; }
 
-static void launch_leaf(int count, DView const *C, DView const *A, DView const *B, bool overwrite, cudaStream_t stream) {
+static void launch_leaf(int count, DView const *C, DView const *A, DView const *B, bool overwrite, cudaStream_t stream,
+                        bool clear_first = false) {
   if (count <= 0 || A[0].nrows <= 0 || A[0].ncols <= 0 || B[0].ncols <= 0) return;   // empty product: C unchanged
   if (count > m4rm_batch_limit(A[0].nrows, A[0].ncols, B[0].ncols))
     die("m4ri_b200: batch of %d leaf products exceeds the limit of this leaf\n", count);
@@ -495,8 +496,10 @@ static void launch_leaf(int count, DView const *C, DView const *A, DView const *
   }
   bool const tall = tall_leaf(A[0].nrows, A[0].ncols, B[0].ncols, overwrite);
   g_last_leaf = tall ? 2 : 1;
+  if (clear_first && !tall)
+    for (int i = 0; i < count; ++i) launch_zero(C[i], stream);
   if (tall)
-    launch_m4rm_leaf2(count, C, A, B, stream);                       // tall tiles: 4096 rows x 256 bits
+    launch_m4rm_leaf2(count, C, A, B, stream, clear_first);          // tall tiles: 4096 rows x 256 bits
   else if (A[0].nrows <= 256)
     launch_variant<256, 256>(count, C, A, B, overwrite, stream);     // short operands: 256-row tiles
   else
@@ -506,6 +509,15 @@ static void launch_leaf(int count, DView const *C, DView const *A, DView const *
 
 void launch_m4rm_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream) {
   launch_leaf(count, C, A, B, false, stream);
+}
+
+void launch_m4rm_batch_clear(int count, DView const *C, DView const *A, DView const *B, cudaStream_t stream) {
+  if (count <= 0 || C[0].nrows <= 0 || C[0].ncols <= 0) return;
+  if (A[0].ncols <= 0) {                                             // empty inner dimension: the product is zero
+    for (int i = 0; i < count; ++i) launch_zero(C[i], stream);
+    return;
+  }
+  launch_leaf(count, C, A, B, false, stream, true);
 }
 
 void launch_m4rm(DView C, DView A, DView B, cudaStream_t stream) { launch_leaf(1, &C, &A, &B, false, stream); }

@@ -121,6 +121,9 @@ L2_FN void red_xor64(unsigned long long *p, uint32_t lo, uint32_t hi) {
   unsigned long long v = (static_cast<unsigned long long>(hi) << 32) | lo;
   asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+L2_FN void stg128(unsigned long long *p, U4 const &v) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 L2_FN void cta_sync() { __syncthreads(); }
 L2_FN uint32_t gate(uint32_t a, uint32_t b, uint32_t c) {   // a | (b & c) as ONE LOP3 the compiler cannot see through
   uint32_t r;
@@ -165,8 +168,9 @@ bool leaf2_suits(int m, int l, int n) {
   return padded * 16 <= (long long)m * 17;            // at most 1/16 of the lookups wasted on padding rows
 }
 
-// C ^= A*B for `count` (<= 7) products of identical shape in one persistent launch.
-void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *B, cudaStream_t stream) {
+// C ^= A*B (overwrite == false) or C = A*B (overwrite == true: C need not be initialised) for `count` (<= 49) products of
+// identical shape in one persistent launch.
+void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *B, cudaStream_t stream, bool overwrite) {
   using namespace leaf2;
   // experiment knobs: M4RI_B200_LEAF2_AWIDE=1 loads the A bits of a whole slab per row with one LDS.128;
   // M4RI_B200_LEAF2_SPLIT=0|1 lets all / half of the warps build the tables of a step
@@ -221,6 +225,20 @@ void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *
   }();
   long long const tiles_total = (long long)p.tiles_m * p.tiles_n * count;
   p.dp_rounds = hybrid ? (int)(tiles_total / grid) : 0;
+  p.store_dp = 0;
+  if (overwrite) {
+    // C = A*B: the tiles of the whole-tile rounds are stored by their single owner, so only the products that contain
+    // tiles of the stream-K tail (the last ones in (product, tile) order) have to start from zeros
+    static int const store = [] {
+      char const *e = getenv("M4RI_B200_LEAF2_STORE");
+      return e && e[0] == '0' ? 0 : 1;
+    }();
+    bool const can_store = store && p.dp_rounds > 0 && Cv[0].ncols % 128 == 0;
+    long long const tiles_per_product = (long long)p.tiles_m * p.tiles_n;
+    int const first_zeroed = can_store ? (int)((long long)p.dp_rounds * grid / tiles_per_product) : 0;
+    for (int i = first_zeroed; i < count; ++i) launch_zero(Cv[i], stream);
+    p.store_dp = can_store ? 1 : 0;
+  }
   kern<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(p);
   M4B_CUDA(cudaGetLastError());
   ++g_kernel_launches;

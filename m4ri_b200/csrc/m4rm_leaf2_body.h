@@ -23,7 +23,7 @@
 // where a CTA is 256 host threads, shared memory an array, TMA / cp.async host copies and the mbarriers and
 // atomics are emulated — so the index arithmetic of this file is tested on the CPU (tests/test_leaf2_emu.py)
 // without being restated.  The includer provides: L2_FN, U4, U2, TMap, lds128, lds64, sts128, prmt,
-// mbar_wait, mbar_expect_tx, tma_load_2d, tma_load_3d, cp_async16, cp_async_wait_all, red_xor64, cta_sync,
+// mbar_wait, mbar_expect_tx, tma_load_2d, tma_load_3d, cp_async16, cp_async_wait_all, red_xor64, stg128, cta_sync,
 // gate(a, b, c) = a | (b & c); lds128 also as lds128<IMM>(addr) = [addr + IMM].
 #pragma once
 #include <stdint.h>
@@ -73,6 +73,8 @@ struct alignas(64) Args {
   long long units_per_problem;   // tiles_m * tiles_n * slabs
   long long total_units;         // < 2^31
   int dp_rounds;                 // whole tiles per CTA handled round-robin before the stream-K tail (see cta_body)
+  int store_dp;                  // 1: C = A*B — the whole-tile rounds STORE their tile (C need not be initialised there);
+                                 //    only the tiles of the stream-K tail are merged with red.xor (into zeros)
   unsigned zero;                 // 0 — a value the compiler cannot know (see gate())
 };
 
@@ -324,6 +326,21 @@ L2_FN void cta_body(Args const &p, uint32_t sbase, int tid, int bid, int nblocks
     {
       U4 const seg = lds128(sSeg);
       int const prob = (int)seg.x, tn = (int)seg.y, row0 = (int)seg.z;
+      if (p.store_dp && region < p.dp_rounds) {
+        // this CTA has multiplied the tile's whole K range: plain 16-byte stores (the launcher only selects this mode
+        // for C rows that end on a 128-bit boundary, so both words of a piece are inside the matrix)
+#pragma unroll
+        for (int j = 0; j < RT; ++j) {
+          int const row = row0 + j * NT + tid;
+          if (row < p.m) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              int const wcol = tn * (kTileBits / 64) + (hl ^ hh) * 2;
+              if (wcol < p.nwordsC) stg128(p.C[prob] + (long long)row * p.pitchC[prob] + wcol, acc[j][hh]);
+            }
+          }
+        }
+      } else
 #pragma unroll
       for (int j = 0; j < RT; ++j) {
         int const row = row0 + j * NT + tid;

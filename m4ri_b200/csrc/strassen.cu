@@ -81,8 +81,8 @@ static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws,
 
 static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s) {
   if (levels == 0) {
-    if (clear) launch_zero(C, s);
-    launch_m4rm(C, A, B, s);
+    if (clear) launch_m4rm_batch_clear(1, &C, &A, &B, s);
+    else       launch_m4rm(C, A, B, s);
     return;
   }
   if (levels == 2 && m4rm_batch_limit(A.nrows / 4, A.ncols / 4, B.ncols / 4) >= 49 && !getenv("M4RI_B200_NO_NODE2")) {
@@ -106,8 +106,7 @@ static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Wor
   DView const X[7] = {a[0], a[1], S[3], a[3], S[0], S[1], S[2]};
   DView const Y[7] = {b[0], b[2], b[3], T[3], T[0], T[1], T[2]};
   if (levels == 1) {
-    launch_zero(Pall, s);
-    launch_m4rm_batch(7, P, X, Y, s);
+    launch_m4rm_batch_clear(7, P, X, Y, s);
   } else {
     for (int i = 0; i < 7; ++i) winograd_node(P[i], X[i], Y[i], levels - 1, true, ws, s);
   }
@@ -175,8 +174,7 @@ static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws,
       P2[7 * i + j] = P2all.sub((7 * i + j) * m4, 0, (7 * i + j + 1) * m4, n4);
     }
   }
-  launch_zero(P2all, s);
-  launch_m4rm_batch(49, P2, X2, Y2, s);
+  launch_m4rm_batch_clear(49, P2, X2, Y2, s);        // P2 = products: no zero fill of the 49 temporaries
   if (fused) {
     DView csub[16];                                  // the 49 products straight into the 16 sub-blocks of C
     for (int q1 = 0; q1 < 4; ++q1) quadrants(c[q1], csub + 4 * q1);

@@ -168,6 +168,10 @@ L2_FN void cp_async_wait_all() {}
 L2_FN void red_xor64(unsigned long long *p, uint32_t lo, uint32_t hi) {
   __atomic_fetch_xor(p, ((unsigned long long)hi << 32) | lo, __ATOMIC_RELAXED);
 }
+L2_FN void stg128(unsigned long long *p, U4 const &v) {
+  p[0] = ((unsigned long long)v.y << 32) | v.x;
+  p[1] = ((unsigned long long)v.w << 32) | v.z;
+}
 L2_FN void cta_sync() { g_cta_barrier.arrive_and_wait(); }
 L2_FN uint32_t gate(uint32_t a, uint32_t b, uint32_t c) { return a | (b & c); }
 
@@ -257,6 +261,20 @@ bool run_case(int count, int m, int l, int n, int nblocks) {
     char const *e = getenv("EMU_HYBRID");
     long long const tiles_total = (long long)p.tiles_m * p.tiles_n * count;
     p.dp_rounds = (e && e[0] == '0') ? 0 : (int)(tiles_total / nblocks);
+    // EMU_STORE=1: the launcher's C = A*B mode — whole-tile rounds store, only the products holding tail tiles start
+    // from zeros, every other product starts from GARBAGE that must be overwritten
+    char const *st = getenv("EMU_STORE");
+    if (st && st[0] == '1' && p.dp_rounds > 0 && n % 128 == 0) {
+      p.store_dp = 1;
+      long long const tpp = (long long)p.tiles_m * p.tiles_n;
+      int const first_zeroed = (int)((long long)p.dp_rounds * nblocks / tpp);
+      for (int i = 0; i < count; ++i) {
+        Mat Z(m, n);
+        W[i] = Z;
+        addmul_definition(W[i], A[i], B[i]);                        // expected: exactly A*B
+        if (i >= first_zeroed) std::fill(C[i].w.begin(), C[i].w.end(), 0);
+      }
+    }
   }
   g_bar_base = kEmuSbase + kOffBar;
 

@@ -40,6 +40,16 @@ def test_hybrid_partition(emu, hybrid, count, m, l, n, blocks):
 
 
 @pytest.mark.parametrize("count,m,l,n,blocks", [
+    (3, 4096, 384, 1024, 5), (7, 4096, 256, 512, 4), (1, 8192, 256, 768, 6), (2, 5000, 300, 384, 3), (49, 4096, 128, 256, 9),
+])
+def test_store_mode_overwrites_uninitialised_tiles(emu, count, m, l, n, blocks):
+    """C = A*B: the whole-tile rounds store their tile over garbage, only the products with stream-K tail tiles are zeroed"""
+    out = subprocess.run([emu, str(count), str(m), str(l), str(n), str(blocks)], capture_output=True, text=True,
+                         timeout=900, env=dict(os.environ, EMU_STORE="1"))
+    assert out.returncode == 0 and "FAIL" not in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("count,m,l,n,blocks", [
     (1, 1, 1, 1, 1),                 # the smallest product
     (1, 4097, 129, 257, 2),          # one past every tile / slab / word edge
     (2, 300, 2000, 100, 9),          # long K, short and narrow C
