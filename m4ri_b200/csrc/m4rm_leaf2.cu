@@ -158,6 +158,9 @@ namespace m4b {
 namespace {
 constexpr int kThreads = 256;
 constexpr int kDefaultSplit = 1;   // tables of a step built by alternating halves of the CTA (+1.2 % measured); 0: by all warps
+constexpr int kDefaultAwide = 1;   // A bits of a whole slab per row with one LDS.128 (4 wavefronts per 32 rows and slab instead
+                                   // of 8: the LDS.64 form has a 2-way bank conflict at its 16-byte stride); needs 32 more live
+                                   // registers, which fit since the kernel compiles without spills (round 2): +1.3 % measured
 }
 
 // The tall tile only pays when its 4096 rows are (nearly) all real rows: rows past m are zero-filled by the
@@ -174,18 +177,18 @@ void launch_m4rm_leaf2(int count, DView const *Cv, DView const *A, DView const *
   using namespace leaf2;
   // experiment knobs: M4RI_B200_LEAF2_AWIDE=1 loads the A bits of a whole slab per row with one LDS.128;
   // M4RI_B200_LEAF2_SPLIT=0|1 lets all / half of the warps build the tables of a step
-  static int const variant = [] {
+  static int const variant = [] {      // bit 0: AWIDE, bit 1: SPLIT
     char const *a = getenv("M4RI_B200_LEAF2_AWIDE"), *s = getenv("M4RI_B200_LEAF2_SPLIT");
-    if (a && a[0] == '1') return 1;
-    if (s && (s[0] == '0' || s[0] == '1')) return s[0] == '1' ? 2 : 0;
-    return kDefaultSplit ? 2 : 0;
+    int const awide = a ? (a[0] == '1') : kDefaultAwide, split = s ? (s[0] == '1') : kDefaultSplit;
+    return awide | (split << 1);
   }();
   static int const l2hint = [] {
     char const *e = getenv("M4RI_B200_LEAF2_L2HINT");
     return e ? atoi(e) & 7 : 0;
   }();
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
-  auto kern = variant == 1 ? m4rm_leaf2_kernel<kThreads, 1, 0>
+  auto kern = variant == 3 ? m4rm_leaf2_kernel<kThreads, 1, 1>
+            : variant == 1 ? m4rm_leaf2_kernel<kThreads, 1, 0>
             : variant == 2 ? m4rm_leaf2_kernel<kThreads, 0, 1> : m4rm_leaf2_kernel<kThreads, 0, 0>;
   int dev = 0;
   M4B_CUDA(cudaGetDevice(&dev));

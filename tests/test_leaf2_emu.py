@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module", params=[(0, 0), (1, 0), (0, 1)], ids=["a-lds64", "a-lds128", "split-build"])
+@pytest.fixture(scope="module", params=[(0, 0), (1, 0), (0, 1), (1, 1)], ids=["a-lds64", "a-lds128", "split-build", "a-lds128-split-build"])
 def emu(request, tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("emu") / "emu_leaf2")
     subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-Wno-unknown-pragmas", f"-DEMU_AWIDE={request.param[0]}", f"-DEMU_SPLIT={request.param[1]}",
