@@ -157,7 +157,8 @@ namespace m4b {
 
 namespace {
 constexpr int kThreads = 256;
-constexpr int kDefaultSplit = 1;   // tables of a step built by alternating halves of the CTA (+1.2 % measured); 0: by all warps
+constexpr int kDefaultSplit = 0;   // 1: tables of a step built by alternating halves of the CTA (+1.2 % with LDS.64 A loads, but -1.7 % together
+                                   // with LDS.128 A loads, where it makes ptxas spill): 65536^3 94.09 ms (AWIDE 1, SPLIT 0) / 94.76 (0, 1) / 95.69 (1, 1)
 constexpr int kDefaultAwide = 1;   // A bits of a whole slab per row with one LDS.128 (4 wavefronts per 32 rows and slab instead
                                    // of 8: the LDS.64 form has a 2-way bank conflict at its 16-byte stride); needs 32 more live
                                    // registers, which fit since the kernel compiles without spills (round 2): +1.3 % measured

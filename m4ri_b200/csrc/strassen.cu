@@ -53,14 +53,19 @@ int strassen_levels(int m, int k, int n, int cutoff) {
 // Workspace: every level is sized as a fused Winograd node (4 + 4 operand sums and 7 product
 // temporaries); the in-place top level of the host path (3 quarter-size temporaries) needs less.
 size_t strassen_workspace_bytes(int m, int k, int n, int levels) {
-  size_t total = 0;
-  for (int lv = 0; lv < levels; ++lv) {
-    m /= 2; k /= 2; n /= 2;
-    // the last level of a two-level node (winograd_node2) holds the temporaries of all seven children at once
-    size_t const live = (levels >= 2 && lv == levels - 1) ? 7 : 1;
-    total += live * (4 * Workspace::bytes_for(m, k) + 4 * Workspace::bytes_for(k, n) + Workspace::bytes_for(7 * m, n));
-  }
-  return total;
+  if (levels <= 0) return 0;
+  int const m2 = m / 2, k2 = k / 2, n2 = n / 2;
+  size_t const sums = 4 * Workspace::bytes_for(m2, k2) + 4 * Workspace::bytes_for(k2, n2);
+  // one level as its own node (winograd_node): 4 + 4 operand sums, 7 product temporaries, then one child at a time
+  size_t const single = sums + Workspace::bytes_for(7 * m2, n2) + strassen_workspace_bytes(m2, k2, n2, levels - 1);
+  if (levels < 2) return single;
+  // two levels as one node (winograd_node2): the level-1 sums, the 28 + 28 level-2 sums and the 49 products live
+  // together; below them one grandchild at a time (or, with M4RI_B200_NO_FUSED2, the seven level-1 results)
+  int const m4 = m2 / 2, k4 = k2 / 2, n4 = n2 / 2;
+  size_t below = strassen_workspace_bytes(m4, k4, n4, levels - 2);
+  if (below < Workspace::bytes_for(7 * m2, n2)) below = Workspace::bytes_for(7 * m2, n2);
+  size_t const pair = sums + 28 * Workspace::bytes_for(m4, k4) + 28 * Workspace::bytes_for(k4, n4) + Workspace::bytes_for(49 * m4, n4) + below;
+  return single > pair ? single : pair;
 }
 
 static void quadrants(DView const &V, DView q[4]) {
@@ -77,7 +82,7 @@ static void quadrants(DView const &V, DView q[4]) {
 //   post  C11 C12 C21 C22 from P1..P7                          (1 fused element-wise launch)
 // Same products as strassen.c's sequence (Winograd's 7-product form), different bookkeeping: more
 // temporaries (HBM is 180 GB), a third of the element-wise traffic and 3-4 launches instead of 29.
-static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws, cudaStream_t s);
+static void winograd_node2(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s);
 
 static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s) {
   if (levels == 0) {
@@ -85,8 +90,11 @@ static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Wor
     else       launch_m4rm(C, A, B, s);
     return;
   }
-  if (levels == 2 && m4rm_batch_limit(A.nrows / 4, A.ncols / 4, B.ncols / 4) >= 49 && !getenv("M4RI_B200_NO_NODE2")) {
-    winograd_node2(C, A, B, clear, ws, s);
+  // two levels at a time wherever the levels pair up: the bottom pair needs the 49-product launch of the tall-tile leaf,
+  // the pairs above it only the fused two-level additions
+  if (levels >= 2 && levels % 2 == 0 && !getenv("M4RI_B200_NO_NODE2") &&
+      (levels > 2 ? getenv("M4RI_B200_NO_UPPER_PAIRS") == nullptr : m4rm_batch_limit(A.nrows / 4, A.ncols / 4, B.ncols / 4) >= 49)) {
+    winograd_node2(C, A, B, levels, clear, ws, s);
     return;
   }
   DView a[4], b[4], c[4];
@@ -114,11 +122,13 @@ static void winograd_node(DView C, DView A, DView B, int levels, bool clear, Wor
   ws.release(mark);
 }
 
-// The last TWO levels as one node: 49 leaf products in ONE persistent launch and the additions of the seven
-// inner nodes batched into single launches.  A leaf launch costs ~35 us of fill and drain whatever its size
-// (every CTA of the stream-K partition ends with its red.xor merge at the same moment), which is 12 % of a
-// 7 x 4096^3 launch but 2 % of a 49 x 4096^3 one — this is what makes one more Strassen level pay.
-static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws, cudaStream_t s) {
+// TWO levels as one node.  Additions: both levels of operand sums in one pass per side (16 sub-blocks in, the 4
+// level-1 sums and the 28 level-2 sums out) and the 49 products straight into the 16 sub-blocks of C
+// (elementwise.cu: winograd_pre2 / post2) — the level-1 operands are not re-read and the seven intermediate results
+// are never written.  Bottom pair (levels == 2): 49 leaf products in ONE persistent launch — a leaf launch costs
+// ~35 us of fill and drain whatever its size, which is 12 % of a 7 x 4096^3 launch but 2 % of a 49 x 4096^3 one; this
+// is what makes one more Strassen level pay.  Pairs above it: the 49 products are Strassen products themselves.
+static void winograd_node2(DView C, DView A, DView B, int levels, bool clear, Workspace &ws, cudaStream_t s) {
   static bool const fused = getenv("M4RI_B200_NO_FUSED2") == nullptr;   // the two-pass form, kept for A/B measurements
   DView a[4], b[4], c[4];
   quadrants(A, a);
@@ -174,7 +184,11 @@ static void winograd_node2(DView C, DView A, DView B, bool clear, Workspace &ws,
       P2[7 * i + j] = P2all.sub((7 * i + j) * m4, 0, (7 * i + j + 1) * m4, n4);
     }
   }
-  launch_m4rm_batch_clear(49, P2, X2, Y2, s);        // P2 = products: no zero fill of the 49 temporaries
+  if (levels == 2) {
+    launch_m4rm_batch_clear(49, P2, X2, Y2, s);      // P2 = products: no zero fill of the 49 temporaries
+  } else {                                           // an upper pair: the 49 products are Strassen products themselves
+    for (int i = 0; i < 49; ++i) winograd_node(P2[i], X2[i], Y2[i], levels - 2, true, ws, s);
+  }
   if (fused) {
     DView csub[16];                                  // the 49 products straight into the 16 sub-blocks of C
     for (int q1 = 0; q1 < 4; ++q1) quadrants(c[q1], csub + 4 * q1);
