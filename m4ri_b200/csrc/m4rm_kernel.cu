@@ -412,6 +412,7 @@ void launch_variant(int count, DView const *Cv, DView const *A, DView const *B, 
 namespace {
 struct LeafProf {
   bool on = false;
+  int  device = -1;      // the events belong to one device: launches on other GPUs (multi.cu's threads) are not timed
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
   size_t used = 0;
   double bitops = 0;
@@ -419,6 +420,7 @@ struct LeafProf {
 }  // namespace
 
 void leaf_profile_begin() {
+  cudaGetDevice(&g_prof.device);
   g_prof.on = true;
   g_prof.used = 0;
   g_prof.bitops = 0;
@@ -483,7 +485,9 @@ static void launch_leaf(int count, DView const *C, DView const *A, DView const *
   if (count > m4rm_batch_limit(A[0].nrows, A[0].ncols, B[0].ncols))
     die("m4ri_b200: batch of %d leaf products exceeds the limit of this leaf\n", count);
   std::pair<cudaEvent_t, cudaEvent_t> *ev = nullptr;
-  if (g_prof.on) {
+  int cur_dev = -1;
+  if (g_prof.on) cudaGetDevice(&cur_dev);
+  if (g_prof.on && cur_dev == g_prof.device) {
     if (g_prof.used == g_prof.pool.size()) {
       std::pair<cudaEvent_t, cudaEvent_t> e;
       M4B_CUDA(cudaEventCreate(&e.first));

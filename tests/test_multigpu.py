@@ -39,3 +39,27 @@ def test_mul_mp_matches_oracle_for_every_device_count(lib, shape, cutoff):
         assert np.array_equal(H.storage(D), H.storage(want_add))
         H.free(C, D)
     H.free(A, B, C0, want_mul, want_add)
+
+
+def test_switching_the_device_between_large_pageable_products(lib):
+    """m4ri_b200_set_device on an initialised library must tear down everything that belongs to the old GPU
+    (workspace, streams, the staging ring with its events, the cached SM count) — a large pageable product on GPU 0,
+    then on GPU 1, then on GPU 0 again."""
+    rng = np.random.default_rng(8)
+    m, l, n = 3000, 9000, 5000            # operands above the 4 MiB staging threshold
+    A, B = H.new(m, l), H.new(l, n)
+    for M in (A, B):
+        st = H.storage(M)
+        st[:, :] = rng.integers(0, 2**64, size=st.shape, dtype=np.uint64)
+        st[:, M.contents.width - 1] &= np.uint64(M.contents.high_bitmask)
+        st[:, M.contents.width:] = 0
+    want = H.oracle().orc_mul(None, A, B, 0)
+    lib.m4ri_b200_set_num_devices(1)
+    for device in (0, 1, 0):
+        lib.m4ri_b200_set_device(device)
+        C = H.new(m, n)
+        lib.mzd_mul(C, A, B, 0)
+        assert np.array_equal(H.storage(C), H.storage(want)), device
+        H.free(C)
+    lib.m4ri_b200_set_device(0)
+    H.free(A, B, want)
