@@ -36,5 +36,46 @@ for (m, n) in [(65, 63), (700, 1300)]:
     T = lib.m4ri_b200_transpose(None, A)
     ok &= H.equal(T, O.orc_transpose(None, A))
     print("transpose", m, n, "OK" if ok else "BAD", flush=True)
+# round 2: the tall-tile leaf with the hybrid partition and store mode under a two-level Strassen node with the fused
+# two-level additions (8192^3 at cutoff 2048 with the tall leaf forced: 49 products of 2048^3 in one launch), and the
+# accumulating form; checked by Freivalds (the scalar oracle is too slow under the sanitizer at this size)
+if os.environ.get("SANITIZE_BIG", "1") == "1":
+    prev = lib.m4ri_b200_set_leaf_variant(2)
+    n = 8192
+    rng = np.random.default_rng(4)
+    A, B, C = H.new(n, n), H.new(n, n), H.new(n, n)
+    for M in (A, B):
+        H.storage(M)[:, :] = rng.integers(0, 2**64, size=H.storage(M).shape, dtype=np.uint64)
+    lib.mzd_mul(C, A, B, 2048)
+    path = lib.m4ri_b200_last_path().decode()
+    Aw, Bw, Cw = (m4ri_b200.valid_words(M) for M in (A, B, C))
+
+    def matvec(M, x):                       # bit-packed M [rows, words] times packed vector x -> packed result
+        anded = M & x[None, :]
+        f = np.bitwise_xor.reduce(anded, axis=1)
+        for sft in (32, 16, 8, 4, 2, 1):
+            f ^= f >> np.uint64(sft)
+        bits = (f & np.uint64(1)).astype(np.uint8)
+        return np.packbits(bits.reshape(-1, 64)[:, ::-1], axis=1, bitorder="big").view(">u8").astype(np.uint64).ravel()
+
+    for _ in range(8):
+        x = rng.integers(0, 2**64, size=n // 64, dtype=np.uint64)
+        ok &= bool(np.array_equal(matvec(Aw, matvec(Bw, x)), matvec(Cw, x)))
+    lib.mzd_addmul(C, A, B, 2048)           # C ^= A*B -> zero
+    ok &= not H.storage(C).any()
+    lib.m4ri_b200_set_leaf_variant(prev)
+    print("big", n, path, "OK" if ok else "BAD", flush=True)
+    # PLE with the cluster strip kernel
+    import ctypes
+    from ctypes import POINTER, c_int
+    from m4ri_b200 import MzpT
+    E = H.random_matrix(1500, 1100)
+    F = H.clone(E)
+    pw, qw = (c_int * 1500)(), (c_int * 1100)()
+    rw = O.orc_ple(F, pw, qw)
+    pv, qv = (c_int * 1500)(), (c_int * 1100)()
+    r = lib.mzd_ple(E, ctypes.byref(MzpT(ctypes.cast(pv, POINTER(c_int)), 1500)), ctypes.byref(MzpT(ctypes.cast(qv, POINTER(c_int)), 1100)), 0)
+    ok &= r == rw and H.equal(E, F) and list(pv) == list(pw)
+    print("ple", r, "OK" if ok else "BAD", flush=True)
 print("ALL OK" if ok else "FAILURES")
 sys.exit(0 if ok else 1)
