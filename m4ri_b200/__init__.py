@@ -115,6 +115,8 @@ def _declare(lib):
     lib.m4ri_b200_dmul_levels.argtypes = [DMatP, DMatP, DMatP, c_int, c_int, c_void_p]
     lib.m4ri_b200_dmul_quads.argtypes = [DMatP * 4, DMatP * 4, DMatP * 4, c_int, c_int, c_void_p, POINTER(Hooks)]
     lib.m4ri_b200_result_free.argtypes = [MzdP]
+    lib.m4ri_b200_dmul_tc.argtypes = [DMatP, DMatP, DMatP, c_int, c_void_p]
+    lib.m4ri_b200_dmul_tc2.argtypes = [DMatP, DMatP, DMatP, c_void_p]
     lib.m4ri_b200_from_str.argtypes, lib.m4ri_b200_from_str.restype = [c_int, c_int, c_char_p], MzdP
     lib.m4ri_b200_from_jcf.argtypes, lib.m4ri_b200_from_jcf.restype = [c_char_p, c_int], MzdP
     lib.m4ri_b200_to_jcf.argtypes, lib.m4ri_b200_to_jcf.restype = [MzdP, c_char_p], c_int

@@ -889,6 +889,19 @@ rci_t m4ri_b200_dple(m4ri_b200_dmat *A, rci_t *P, rci_t *Q, void *stream) {
   return ple_device(as_view(A), P, Q, co, c.ws, stream ? static_cast<cudaStream_t>(stream) : c.stream);
 }
 
+// EXPERIMENTAL (measurement only): C (^)= A * B on the tensor cores; Bt = B transposed (m4ri_b200_dtranspose)
+void m4ri_b200_dmul_tc(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *Bt, int clear, void *stream) {
+  M4B_LOCKED;
+  ctx();
+  launch_tc_leaf_simple(as_view(C), as_view(A), as_view(Bt), clear == 0, stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+}
+
+void m4ri_b200_dmul_tc2(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {
+  M4B_LOCKED;
+  ctx();
+  launch_tc_leaf2(as_view(C), as_view(A), as_view(B), stream ? static_cast<cudaStream_t>(stream) : ctx().stream);
+}
+
 void m4ri_b200_dadd(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream) {
   M4B_LOCKED;
   if (A->nrows != B->nrows || A->ncols != B->ncols || C->nrows != A->nrows || C->ncols != A->ncols)

@@ -125,6 +125,10 @@ size_t trsm_workspace_bytes(int t, int m, int n, int cutoff);
 int    echelonize_device(DView A, Workspace &ws, cudaStream_t s);     // in place, returns the rank, synchronises s
 size_t echelon_workspace_bytes(int m, int n, int64_t pitch_words = 0);   // pitch_words: A's pitch if above the minimal one
 
+// ---- experimental tensor-core leaf (tc_leaf.cu): C (^)= A * Bt^T with tcgen05.mma kind::mxf4 on expanded operands ----
+void launch_tc_leaf_simple(DView C, DView A, DView Bt, bool accumulate, cudaStream_t s);
+void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s);        // pipelined B-stationary form, C = A * B
+
 // ---- PLE decomposition (ple.cu) ----------------------------------------------------------------
 // in place on a device-resident matrix; P (nrows ints) and Q (ncols ints) on the host; returns the rank, synchronises s
 int    ple_device(DView A, int *P, int *Q, int cutoff, Workspace &ws, cudaStream_t s);

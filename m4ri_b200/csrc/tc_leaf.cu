@@ -1,0 +1,417 @@
+// tc_leaf.cu — EXPERIMENTAL tensor-core leaf (not on any default path; m4ri_b200_dmul_tc only).
+//
+// C (^)= A * B over GF(2) on the 5th-generation tensor cores: the bits of A (rows) and of B^T (rows = columns of B) are
+// expanded to e2m1 nibbles (0 -> 0x0, 1 -> 0x2 = 1.0) in shared memory, multiplied with
+// tcgen05.mma.kind::mxf4.block_scale (unit ue8m0 scales, fp32 accumulators in TMEM, exact for 0/1 operands: integer
+// sums < 2^24 — profiles/r02_tensor_core_question.md), and the parity of every accumulator is packed back into the
+// bit-packed C.  This first form is output-stationary and single-buffered — it exists to validate the data path
+// (nibble layout, descriptors, mbarrier phases, parity epilogue) bit for bit against the M4RM leaf, not to be fast.
+// Shapes: m % 128 == 0, n % 256 == 0, l % 128 == 0; Bt is B transposed (n x l).
+#include <cuda_runtime.h>
+
+#include "dev.h"
+
+namespace m4b {
+namespace {
+
+constexpr int kM = 128, kN = 256, kKBytes = 64;            // one K chunk: 128 elements = 64 bytes of e2m1 per row
+constexpr int kSBO = kKBytes / 16 * 128;                   // bytes between 8-row groups of the canonical no-swizzle layout
+
+__device__ __forceinline__ uint32_t smem_u32(void const *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;              // LBO: next core matrix along K
+  d |= (uint64_t)(((uint32_t)kSBO >> 4) & 0x3FFF) << 32;    // SBO: next 8-row group
+  d |= (uint64_t)1 << 46;                                    // descriptor version (Blackwell)
+  return d;
+}
+
+// eight bits -> eight e2m1 nibbles (bit e -> nibble e: 0x2 where the bit is set)
+__device__ __forceinline__ uint32_t expand8(uint32_t b) {
+  uint32_t x = b & 0xFFu;
+  x = (x | (x << 12)) & 0x000F000Fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x << 1;
+}
+
+// rows [row0, row0 + nrows) of a bit-packed matrix, K bits [k0, k0 + 128) -> the shared-memory operand image
+__device__ __forceinline__ void expand_rows(uint8_t *simg, word const *M, long long pitch, int row0, int nrows, int k0, int tid,
+                                            int nthreads) {
+  for (int r = tid; r < nrows; r += nthreads) {
+    word const *src = M + (long long)(row0 + r) * pitch + k0 / 64;
+    unsigned long long const w0 = src[0], w1 = src[1];
+    uint8_t *dst = simg + (r / 8) * kSBO + (r % 8) * 16;
+#pragma unroll
+    for (int beta = 0; beta < 16; ++beta) {                 // packed byte beta -> e2m1 bytes 4 beta .. 4 beta + 3
+      uint32_t const b = (uint32_t)((beta < 8 ? w0 >> (8 * beta) : w1 >> (8 * (beta - 8))) & 0xFFull);
+      int const kb = 4 * beta;
+      *reinterpret_cast<uint32_t *>(dst + (kb / 16) * 128 + kb % 16) = expand8(b);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 1) tc_leaf_simple_kernel(word *C, long long pitchC, word const *A, long long pitchA,
+                                                                word const *Bt, long long pitchB, int l, int accumulate) {
+  __shared__ __align__(1024) uint8_t sA[kM * kKBytes];
+  __shared__ __align__(1024) uint8_t sB[kN * kKBytes];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  int const tid = threadIdx.x, warp = tid >> 5;
+  int const m0 = blockIdx.y * kM, n0 = blockIdx.x * kN;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t const tmem = tmem_base;
+  {   // unit scales: every byte of TMEM columns 256..511 = 0x7F (ue8m0 2^0)
+    uint32_t const v = 0x7F7F7F7Fu;
+    for (int c = 256; c < 512; c += 8) {
+      uint32_t const taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  uint32_t const idesc = (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | (1u << 23) | ((uint32_t)(kM >> 4) << 24);
+  int const chunks = l / 128;
+  for (int ch = 0; ch < chunks; ++ch) {
+    expand_rows(sA, A, pitchA, m0, kM, ch * 128, tid, 128);
+    expand_rows(sB, Bt, pitchB, n0, kN, ch * 128, tid, 128);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+      uint64_t const da = make_desc(smem_u32(sA)), db = make_desc(smem_u32(sB));
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint64_t const a = da + (uint64_t)((ks * 256) >> 4), b = db + (uint64_t)((ks * 256) >> 4);
+        uint32_t const acc = (ch | ks) ? 1u : 0u;
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                     "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}"
+                     ::"r"(tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(tmem + 256u), "r"(tmem + 384u) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    {   // the MMAs of this chunk have read the operand images: they may be overwritten (single buffer)
+      uint32_t const b = smem_u32(&bar), parity = (uint32_t)(ch & 1);
+      asm volatile(
+          "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(b),
+          "r"(parity)
+          : "memory");
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  // ---- epilogue: parity of every accumulator -> one bit of C.  Warp w owns TMEM lanes (= tile rows) 32 w .. 32 w + 31.
+  uint32_t *crow = reinterpret_cast<uint32_t *>(C + (long long)(m0 + tid) * pitchC) + n0 / 32;
+  for (int c = 0; c < kN; c += 32) {
+    uint32_t v[32];
+    uint32_t const taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bits |= ((uint32_t)__float2int_rn(__uint_as_float(v[j])) & 1u) << j;
+    if (accumulate) crow[c / 32] ^= bits;
+    else            crow[c / 32] = bits;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+}  // namespace
+
+// C (m x n) (^)= A (m x l) * Bt^T, Bt = B transposed (n x l); experimental, see the file header
+void launch_tc_leaf_simple(DView C, DView A, DView Bt, bool accumulate, cudaStream_t s) {
+  if (A.nrows % kM || Bt.nrows % kN || A.ncols % 128 || A.ncols != Bt.ncols || C.nrows != A.nrows || C.ncols != Bt.nrows)
+    die("m4ri_b200_dmul_tc: needs m %% 128 == 0, n %% 256 == 0, l %% 128 == 0 and Bt = B^T\n");
+  dim3 const grid(Bt.nrows / kN, A.nrows / kM);
+  tc_leaf_simple_kernel<<<grid, 128, 0, s>>>(C.data, C.pitch, A.data, A.pitch, Bt.data, Bt.pitch, A.ncols, accumulate ? 1 : 0);
+  M4B_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+}
+
+}  // namespace m4b
+
+// =====================================================================================================================
+// Second form: B-stationary, pipelined, warp-specialised.  The operands are expanded to e2m1 ONCE by a streaming
+// pre-pass into "images" whose pieces are exactly the shared-memory operand layout, so the main kernel moves them with
+// plain bulk copies (cp.async.bulk + mbarrier complete_tx):
+//   A image:  [row tile of 128][K chunk of 1024][sub 0..3] x 16 KB   (sub-image = 128 rows x 256 elements)
+//   B image:  [column panel of 256][K chunk][sub 0..3]     x 32 KB   (rows = columns of B, from B^T)
+// A job = (product, K chunk, column panel): the 128 KB panel chunk stays in shared memory while EVERY row tile of A
+// streams past it through a ring of 16 KB stages (4 KB of L2 traffic per 128-cycle MMA pair = 31 B/clk/SM, under the L2
+// slice cap; the output-stationary form needs 3x that).  Per row tile: 16 K-steps x two N=128 MMAs into two of three
+// 128-column TMEM accumulators; eight epilogue warps drain them (parity by the 2^23 trick), and XOR the 128 x 128-bit
+// result into C with red.global (partial sums over K chunks combine by XOR, so C starts zeroed).
+// =====================================================================================================================
+namespace m4b {
+namespace {
+
+constexpr int kStageBytes = 16384, kBSubBytes = 32768, kSubs = 4, kAStages = 5;
+constexpr int kPanelBytes = kSubs * kBSubBytes;
+constexpr int kTc2Threads = 320;
+constexpr int kTc2Smem = kPanelBytes + kAStages * kStageBytes + 256 + 1024;
+constexpr int kTcMaxBatch = 49;
+
+struct Tc2Args {
+  word *C[kTcMaxBatch];
+  uint8_t const *imgA[kTcMaxBatch];
+  uint8_t const *imgB[kTcMaxBatch];
+  long long pitchC;
+  int count, mtiles, nkc, npanels;
+};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  long long const t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000ll) __trap();     // a protocol bug must not hang the box
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, void const *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc2(uint32_t saddr) {      // sub-image layout: LBO 128, SBO 1024
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46);
+}
+
+__global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_constant__ Tc2Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint32_t const base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint32_t const sB = base, sA = base + kPanelBytes, bars = sA + kAStages * kStageBytes;
+  // barriers (8 bytes each): full_a[5] empty_a[5] full_b empty_b acc_full[3] acc_empty[3]
+  auto full_a = [&](int s) { return bars + 8u * s; };
+  auto empty_a = [&](int s) { return bars + 8u * (kAStages + s); };
+  uint32_t const full_b = bars + 8u * (2 * kAStages), empty_b = full_b + 8u;
+  auto acc_full = [&](int b) { return empty_b + 8u + 8u * b; };
+  auto acc_empty = [&](int b) { return empty_b + 8u + 8u * (3 + b); };
+  __shared__ uint32_t tmem_slot;
+  int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kAStages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a(s)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty_a(s)));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_b));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty_b));
+    for (int b = 0; b < 3; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(acc_full(b)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(acc_empty(b)));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t const tmem = tmem_slot;
+  if (warp >= 2 && warp < 6) {   // unit ue8m0 scales in columns 384..511 of every lane
+    uint32_t const v = 0x7F7F7F7Fu;
+    for (int c = 384; c < 512; c += 8) {
+      uint32_t const taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c;
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  int const jobs_per_product = args.nkc * args.npanels, njobs = args.count * jobs_per_product;
+  if (warp == 0) {
+    if (lane == 0) {             // ---------------- producer ----------------
+      uint32_t a_it = 0, ji = 0;
+      for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
+        int const p = job / jobs_per_product, rem = job % jobs_per_product, kc = rem / args.npanels, np = rem % args.npanels;
+        mbar_wait(empty_b, (ji & 1u) ^ 1u);
+        mbar_expect_tx(full_b, kPanelBytes);
+        uint8_t const *srcB = args.imgB[p] + ((long long)(np * args.nkc + kc) * kSubs) * kBSubBytes;
+        for (int s = 0; s < kSubs; ++s) bulk_g2s(sB + s * kBSubBytes, srcB + (long long)s * kBSubBytes, kBSubBytes, full_b);
+        for (int mt = 0; mt < args.mtiles; ++mt) {
+          uint8_t const *srcA = args.imgA[p] + ((long long)(mt * args.nkc + kc) * kSubs) * kStageBytes;
+          for (int s = 0; s < kSubs; ++s, ++a_it) {
+            uint32_t const st = a_it % kAStages;
+            mbar_wait(empty_a(st), ((a_it / kAStages) & 1u) ^ 1u);
+            mbar_expect_tx(full_a(st), kStageBytes);
+            bulk_g2s(sA + st * kStageBytes, srcA + (long long)s * kStageBytes, kStageBytes, full_a(st));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {             // ---------------- MMA issue ----------------
+      uint32_t const idesc = (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (1u << 23) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t const sfa = tmem + 384u, sfb = tmem + 448u;
+      uint32_t a_it = 0, ji = 0, tile_ctr = 0;
+      for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
+        mbar_wait(full_b, ji & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
+          uint32_t const u0 = 2u * tile_ctr, u1 = u0 + 1u, b0 = u0 % 3u, b1 = u1 % 3u;
+          for (int s = 0; s < kSubs; ++s, ++a_it) {
+            uint32_t const st = a_it % kAStages;
+            mbar_wait(full_a(st), (a_it / kAStages) & 1u);
+            if (s == 0) mbar_wait(acc_empty(b0), ((u0 / 3u) & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint64_t const da = make_desc2(sA + st * kStageBytes), db = make_desc2(sB + s * kBSubBytes);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              if (half == 1 && s == 0) {
+                mbar_wait(acc_empty(b1), ((u1 / 3u) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              }
+              uint32_t const d = tmem + (half ? b1 : b0) * 128u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint64_t const a = da + (uint64_t)((j * 256) >> 4), b = db + (uint64_t)((half * 16384 + j * 256) >> 4);
+                uint32_t const acc = (s | j) ? 1u : 0u;
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                             "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}"
+                             ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb) : "memory");
+              }
+            }
+            tc_commit(empty_a(st));
+          }
+          tc_commit(acc_full(b0));
+          tc_commit(acc_full(b1));
+        }
+        tc_commit(empty_b);
+      }
+    }
+  } else {                       // ---------------- epilogue: warps 2..9 ----------------
+    int const q = warp & 3, h = (warp - 2) >> 2;
+    uint32_t tile_ctr = 0;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+      int const p = job / jobs_per_product, np = (job % jobs_per_product) % args.npanels;
+      for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
+        uint32_t const u = 2u * tile_ctr + (uint32_t)h, b = u % 3u;
+        mbar_wait(acc_full(b), (u / 3u) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t const taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128u + (uint32_t)(c * 32);
+          uint32_t *o = v + 32 * c;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]), "=r"(o[9]),
+                "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15]), "=r"(o[16]), "=r"(o[17]), "=r"(o[18]),
+                "=r"(o[19]), "=r"(o[20]), "=r"(o[21]), "=r"(o[22]), "=r"(o[23]), "=r"(o[24]), "=r"(o[25]), "=r"(o[26]), "=r"(o[27]),
+                "=r"(o[28]), "=r"(o[29]), "=r"(o[30]), "=r"(o[31])
+              : "r"(taddr));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(b));
+        unsigned long long out[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          unsigned long long bits = 0;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            float const f = __uint_as_float(v[64 * w + j]) + 8388608.0f;     // integer value -> low mantissa bits
+            bits |= (unsigned long long)(__float_as_uint(f) & 1u) << j;
+          }
+          out[w] = bits;
+        }
+        word *dst = args.C[p] + (long long)(mt * 128 + q * 32 + lane) * args.pitchC + (np * 256 + h * 128) / 64;
+        asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(dst), "l"(out[0]) : "memory");
+        asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(dst + 1), "l"(out[1]) : "memory");
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// bits of M (rows x K) -> the tiled e2m1 image; one thread per 16-byte core-matrix row (32 elements)
+__global__ void tc_expand_kernel(uint4 *img, word const *M, long long pitch, int R, int nkc, long long total) {
+  long long const o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= total) return;
+  long long const sub = o / (R * 8);
+  int const within = (int)(o % (R * 8)), rg = within / 64, kg = (within / 8) % 8, r8 = within % 8;
+  int const s = (int)(sub % kSubs), kc = (int)((sub / kSubs) % nkc);
+  long long const tile = sub / ((long long)kSubs * nkc);
+  long long const row = tile * R + rg * 8 + r8;
+  uint32_t const bits = reinterpret_cast<uint32_t const *>(M + row * pitch)[kc * 32 + s * 8 + kg];
+  img[o] = make_uint4(expand8(bits), expand8(bits >> 8), expand8(bits >> 16), expand8(bits >> 24));
+}
+
+struct TcScratch { uint8_t *imgA = nullptr, *imgB = nullptr; word *bt = nullptr; size_t a = 0, b = 0, t = 0; int device = -1; };
+TcScratch g_tc;
+
+}  // namespace
+
+// C = A * B (C is overwritten), experimental B-stationary tensor-core form; m % 128 == 0, l % 1024 == 0, n % 256 == 0
+void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) {
+  int const m = A.nrows, l = A.ncols, n = B.ncols;
+  if (m % 128 || l % 1024 || n % 256 || B.nrows != l || C.nrows != m || C.ncols != n)
+    die("m4ri_b200_dmul_tc2: needs m %% 128 == 0, l %% 1024 == 0, n %% 256 == 0\n");
+  size_t const need_a = (size_t)m * l / 2, need_b = (size_t)n * l / 2, need_t = (size_t)n * (l / 64) * sizeof(word);
+  int dev = 0;
+  M4B_CUDA(cudaGetDevice(&dev));
+  if (g_tc.device != dev || g_tc.a < need_a || g_tc.b < need_b || g_tc.t < need_t) {
+    M4B_CUDA(cudaDeviceSynchronize());
+    if (g_tc.imgA) cudaFree(g_tc.imgA);
+    if (g_tc.imgB) cudaFree(g_tc.imgB);
+    if (g_tc.bt) cudaFree(g_tc.bt);
+    M4B_CUDA(cudaMalloc(&g_tc.imgA, need_a));
+    M4B_CUDA(cudaMalloc(&g_tc.imgB, need_b));
+    M4B_CUDA(cudaMalloc(&g_tc.bt, need_t));
+    g_tc.a = need_a; g_tc.b = need_b; g_tc.t = need_t; g_tc.device = dev;
+  }
+  DView Bt{g_tc.bt, (long long)(l / 64), n, l};
+  launch_transpose(Bt, B, s);
+  int const nkc = l / 1024;
+  long long const ta = (long long)need_a / 16, tb = (long long)need_b / 16;
+  tc_expand_kernel<<<(unsigned)((ta + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(g_tc.imgA), A.data, A.pitch, 128, nkc, ta);
+  tc_expand_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(g_tc.imgB), Bt.data, Bt.pitch, 256, nkc, tb);
+  M4B_CUDA(cudaMemset2DAsync(C.data, C.pitch * sizeof(word), 0, (size_t)(n / 64) * sizeof(word), m, s));
+  Tc2Args args{};
+  args.C[0] = C.data; args.imgA[0] = g_tc.imgA; args.imgB[0] = g_tc.imgB;
+  args.pitchC = C.pitch; args.count = 1; args.mtiles = m / 128; args.nkc = nkc; args.npanels = n / 256;
+  static bool attr = false;
+  if (!attr) { M4B_CUDA(cudaFuncSetAttribute(tc_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem)); attr = true; }
+  int const njobs = args.nkc * args.npanels, grid = njobs < m4rm_num_sms() ? njobs : m4rm_num_sms();
+  tc_leaf2_kernel<<<grid, kTc2Threads, kTc2Smem, s>>>(args);
+  M4B_CUDA(cudaGetLastError());
+  g_kernel_launches += 5;
+}
+
+}  // namespace m4b
