@@ -9,6 +9,8 @@
 // Shapes: m % 128 == 0, n % 256 == 0, l % 128 == 0; Bt is B transposed (n x l).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "dev.h"
 
 namespace m4b {
@@ -176,15 +178,15 @@ struct Tc2Args {
   uint8_t const *imgA[kTcMaxBatch];
   uint8_t const *imgB[kTcMaxBatch];
   long long pitchC;
-  int count, mtiles, nkc, npanels;
+  int count, mtiles, nkc, npanels, flags;   // flags: experiment bits (1 skip the parity math)
 };
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   long long const t0 = clock64();
   for (;;) {
     uint32_t done;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.b32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
     if (done) return;
     if (clock64() - t0 > 4000000000ll) __trap();     // a protocol bug must not hang the box
   }
@@ -200,9 +202,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, void const *src, uint32_t
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc2(uint32_t saddr) {      // sub-image layout: LBO 128, SBO 1024
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46);
 }
 
 __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_constant__ Tc2Args args) {
@@ -271,59 +270,83 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {             // ---------------- MMA issue ----------------
-      uint32_t const idesc = (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (1u << 23) | ((uint32_t)(128 >> 4) << 24);
-      uint32_t const sfa = tmem + 384u, sfb = tmem + 448u;
-      uint32_t a_it = 0, ji = 0, tile_ctr = 0;
-      for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
-        mbar_wait(full_b, ji & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
-          uint32_t const u0 = 2u * tile_ctr, u1 = u0 + 1u, b0 = u0 % 3u, b1 = u1 % 3u;
-          for (int s = 0; s < kSubs; ++s, ++a_it) {
-            uint32_t const st = a_it % kAStages;
-            mbar_wait(full_a(st), (a_it / kAStages) & 1u);
-            if (s == 0) mbar_wait(acc_empty(b0), ((u0 / 3u) & 1u) ^ 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint64_t const da = make_desc2(sA + st * kStageBytes), db = make_desc2(sB + s * kBSubBytes);
+  } else if (warp == 1) {        // ---------------- MMA issue ----------------
+    // The whole warp walks the loops (so that the address arithmetic stays in uniform registers — the instruction stream
+    // of the one issuing lane must cost well under the time an MMA occupies the pipe); lane 0 issues.
+    // TMEM: three 128-column regions R0 R1 R2 (+ the scale columns from 384).  An even row tile accumulates in R0|R1, an
+    // odd one in R1|R2, so the K-steps of sub-images 1..3 are single N = 256 instructions; the first sub-image
+    // is issued as N = 128 halves, the half in the region nobody else uses first, so that the drain of R1 (the previous
+    // tile's other half) hides behind 256 cycles of work.
+    uint32_t const idesc128 = (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (1u << 23) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t const idesc256 = (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | (1u << 23) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t const sfa = tmem + 384u, sfb = tmem + 416u;
+    uint32_t const desc_hi = (1024u >> 4) | (1u << 14), lbo = (128u >> 4) << 16;     // SBO, descriptor version | LBO
+    bool const issuer = lane == 0;
+    uint32_t a_it = 0, ji = 0, tile_ctr = 0;
+    auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
+      if (accumulate)
+        asm volatile("{\n.reg .b64 da, db;\n.reg .pred p;\nmov.b64 da, {%1, %6};\nmov.b64 db, {%2, %6};\nsetp.eq.b32 p, 0, 0;\n"
+                     "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], p;\n}"
+                     ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(sfa), "r"(sfb), "r"(desc_hi) : "memory");
+      else
+        asm volatile("{\n.reg .b64 da, db;\n.reg .pred p;\nmov.b64 da, {%1, %6};\nmov.b64 db, {%2, %6};\nsetp.ne.b32 p, 0, 0;\n"
+                     "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], p;\n}"
+                     ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(sfa), "r"(sfb), "r"(desc_hi) : "memory");
+    };
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
+      mbar_wait(full_b, ji & 1u);
+      for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
+        uint32_t const odd = tile_ctr & 1u, rfree = odd ? 2u : 0u;        // this tile: regions {rfree, 1}
+        uint32_t const dbase = tmem + odd * 128u;                          // panel column c <-> TMEM column odd * 128 + c
+        uint32_t const hfree = odd ? 1u : 0u, hmid = hfree ^ 1u;           // panel halves living in rfree / R1
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              if (half == 1 && s == 0) {
-                mbar_wait(acc_empty(b1), ((u1 / 3u) & 1u) ^ 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              }
-              uint32_t const d = tmem + (half ? b1 : b0) * 128u;
+        for (int s = 0; s < kSubs; ++s, ++a_it) {
+          uint32_t const st = a_it % kAStages;
+          mbar_wait(full_a(st), (a_it / kAStages) & 1u);
+          if (s == 0) mbar_wait(acc_empty(rfree), ((tile_ctr >> 1) & 1u) ^ 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t const a_lo = ((sA + st * kStageBytes) >> 4) | lbo, b_lo = ((sB + s * kBSubBytes) >> 4) | lbo;
+          if (s == 0) {
+            if (issuer) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint64_t const a = da + (uint64_t)((j * 256) >> 4), b = db + (uint64_t)((half * 16384 + j * 256) >> 4);
-                uint32_t const acc = (s | j) ? 1u : 0u;
-                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                             "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}"
-                             ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb) : "memory");
-              }
+              for (int j = 0; j < 4; ++j) mma(tmem + rfree * 128u, a_lo + 16u * j, b_lo + hfree * 1024u + 16u * j, idesc128, j != 0);
             }
+            mbar_wait(acc_empty(1), (tile_ctr & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (issuer) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) mma(tmem + 128u, a_lo + 16u * j, b_lo + hmid * 1024u + 16u * j, idesc128, j != 0);
+              tc_commit(empty_a(st));
+            }
+          } else if (issuer) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma(dbase, a_lo + 16u * j, b_lo + 16u * j, idesc256, true);
             tc_commit(empty_a(st));
           }
-          tc_commit(acc_full(b0));
-          tc_commit(acc_full(b1));
         }
-        tc_commit(empty_b);
+        if (issuer) {
+          tc_commit(acc_full(1));
+          tc_commit(acc_full(rfree));
+        }
       }
+      if (issuer) tc_commit(empty_b);
     }
   } else {                       // ---------------- epilogue: warps 2..9 ----------------
-    int const q = warp & 3, h = (warp - 2) >> 2;
+    // group 0 (warps 2..5) always drains R1 — the region every tile needs again —, group 1 (warps 6..9) R0 / R2 in turn
+    int const q = warp & 3, g = (warp - 2) >> 2;
     uint32_t tile_ctr = 0;
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
       int const p = job / jobs_per_product, np = (job % jobs_per_product) % args.npanels;
       for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
-        uint32_t const u = 2u * tile_ctr + (uint32_t)h, b = u % 3u;
-        mbar_wait(acc_full(b), (u / 3u) & 1u);
+        uint32_t const odd = tile_ctr & 1u;
+        uint32_t const region = g == 0 ? 1u : (odd ? 2u : 0u);
+        uint32_t const h = g == 0 ? (odd ^ 1u) : odd;                     // the panel half this region holds for this tile
+        mbar_wait(acc_full(region), g == 0 ? (tile_ctr & 1u) : ((tile_ctr >> 1) & 1u));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v[128];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t const taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128u + (uint32_t)(c * 32);
+          uint32_t const taddr = tmem + ((uint32_t)(q * 32) << 16) + region * 128u + (uint32_t)(c * 32);
           uint32_t *o = v + 32 * c;
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -337,21 +360,22 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(b));
-        unsigned long long out[2];
+        if (lane == 0) mbar_arrive(acc_empty(region));
+        if (args.flags & 1) continue;
+        uint32_t out[4];
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          unsigned long long bits = 0;
+        for (int w = 0; w < 4; ++w) {
+          uint32_t bits = 0;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            float const f = __uint_as_float(v[64 * w + j]) + 8388608.0f;     // integer value -> low mantissa bits
-            bits |= (unsigned long long)(__float_as_uint(f) & 1u) << j;
+          for (int j = 31; j >= 0; --j) {                                   // integer value + 2^23 -> parity in mantissa bit 0
+            float const f = __uint_as_float(v[32 * w + j]) + 8388608.0f;
+            bits = bits * 2u + (__float_as_uint(f) & 1u);
           }
           out[w] = bits;
         }
-        word *dst = args.C[p] + (long long)(mt * 128 + q * 32 + lane) * args.pitchC + (np * 256 + h * 128) / 64;
-        asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(dst), "l"(out[0]) : "memory");
-        asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(dst + 1), "l"(out[1]) : "memory");
+        word *dst = args.C[p] + (long long)(mt * 128 + q * 32 + lane) * args.pitchC + (np * 256 + (int)h * 128) / 64;
+        asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(dst), "l"((unsigned long long)out[0] | ((unsigned long long)out[1] << 32)) : "memory");
+        asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(dst + 1), "l"((unsigned long long)out[2] | ((unsigned long long)out[3] << 32)) : "memory");
       }
     }
   }
@@ -397,17 +421,24 @@ void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) {
     g_tc.a = need_a; g_tc.b = need_b; g_tc.t = need_t; g_tc.device = dev;
   }
   DView Bt{g_tc.bt, (long long)(l / 64), n, l};
-  launch_transpose(Bt, B, s);
   int const nkc = l / 1024;
   long long const ta = (long long)need_a / 16, tb = (long long)need_b / 16;
-  tc_expand_kernel<<<(unsigned)((ta + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(g_tc.imgA), A.data, A.pitch, 128, nkc, ta);
-  tc_expand_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(g_tc.imgB), Bt.data, Bt.pitch, 256, nkc, tb);
+  static int const reuse = getenv("M4RI_B200_TC_REUSE") ? atoi(getenv("M4RI_B200_TC_REUSE")) : 0;   // timing knob: keep the images
+  static word const *last_a = nullptr, *last_b = nullptr;
+  if (!(reuse && last_a == A.data && last_b == B.data)) {
+    launch_transpose(Bt, B, s);
+    tc_expand_kernel<<<(unsigned)((ta + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(g_tc.imgA), A.data, A.pitch, 128, nkc, ta);
+    tc_expand_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(g_tc.imgB), Bt.data, Bt.pitch, 256, nkc, tb);
+    last_a = A.data; last_b = B.data;
+  }
   M4B_CUDA(cudaMemset2DAsync(C.data, C.pitch * sizeof(word), 0, (size_t)(n / 64) * sizeof(word), m, s));
   Tc2Args args{};
   args.C[0] = C.data; args.imgA[0] = g_tc.imgA; args.imgB[0] = g_tc.imgB;
   args.pitchC = C.pitch; args.count = 1; args.mtiles = m / 128; args.nkc = nkc; args.npanels = n / 256;
   static bool attr = false;
   if (!attr) { M4B_CUDA(cudaFuncSetAttribute(tc_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem)); attr = true; }
+  static int const flags = getenv("M4RI_B200_TC_FLAGS") ? atoi(getenv("M4RI_B200_TC_FLAGS")) : 0;
+  args.flags = flags;
   int const njobs = args.nkc * args.npanels, grid = njobs < m4rm_num_sms() ? njobs : m4rm_num_sms();
   tc_leaf2_kernel<<<grid, kTc2Threads, kTc2Smem, s>>>(args);
   M4B_CUDA(cudaGetLastError());

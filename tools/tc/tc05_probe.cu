@@ -9,6 +9,7 @@
 // The same 128 x 64-byte A tile and 256 x 64-byte B tile are multiplied over and over (no global traffic in the timed
 // loop), one elected thread issues, completion through tcgen05.commit -> mbarrier, accumulators read back with
 // tcgen05.ld (32x32b) and compared on the host for a single pass.
+// -DPROBE_N=128 measures the N = 128 shape (the rate per instruction halves, the A tile is re-read twice as often).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tc05_probe tc05_probe.cu ; SASS: cuobjdump -sass tc05_probe
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,7 +18,10 @@
 
 #include <vector>
 
-constexpr int kM = 128, kN = 256, kKBytes = 64, kKStep = 32;   // 8 + 16 KB of static shared memory
+#ifndef PROBE_N
+#define PROBE_N 256
+#endif
+constexpr int kM = 128, kN = PROBE_N, kKBytes = 64, kKStep = 32;   // 8 + 16 KB of static shared memory
 constexpr int kSBO = kKBytes / 16 * 128;                         // bytes between 8-row groups: all K core matrices of a group
 
 __device__ __forceinline__ uint32_t smem_u32(void const *p) { return (uint32_t)__cvta_generic_to_shared(p); }
