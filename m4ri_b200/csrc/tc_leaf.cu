@@ -181,15 +181,21 @@ struct Tc2Args {
   int count, mtiles, nkc, npanels, flags;   // flags: experiment bits (1 skip the parity math)
 };
 
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   long long const t0 = clock64();
   for (;;) {
     uint32_t done;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.b32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) return;
     if (clock64() - t0 > 4000000000ll) __trap();     // a protocol bug must not hang the box
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  if (!done) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
   int const jobs_per_product = args.nkc * args.npanels, njobs = args.count * jobs_per_product;
   if (warp == 0) {
     if (lane == 0) {             // ---------------- producer ----------------
-      uint32_t a_it = 0, ji = 0;
+      uint32_t a_stage = 0, a_phase = 0, ji = 0;
       for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
         int const p = job / jobs_per_product, rem = job % jobs_per_product, kc = rem / args.npanels, np = rem % args.npanels;
         mbar_wait(empty_b, (ji & 1u) ^ 1u);
@@ -261,9 +267,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         for (int s = 0; s < kSubs; ++s) bulk_g2s(sB + s * kBSubBytes, srcB + (long long)s * kBSubBytes, kBSubBytes, full_b);
         for (int mt = 0; mt < args.mtiles; ++mt) {
           uint8_t const *srcA = args.imgA[p] + ((long long)(mt * args.nkc + kc) * kSubs) * kStageBytes;
-          for (int s = 0; s < kSubs; ++s, ++a_it) {
-            uint32_t const st = a_it % kAStages;
-            mbar_wait(empty_a(st), ((a_it / kAStages) & 1u) ^ 1u);
+          for (int s = 0; s < kSubs; ++s) {
+            uint32_t const st = a_stage;
+            mbar_wait(empty_a(st), a_phase ^ 1u);
+            if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1u; }
             mbar_expect_tx(full_a(st), kStageBytes);
             bulk_g2s(sA + st * kStageBytes, srcA + (long long)s * kStageBytes, kStageBytes, full_a(st));
           }
@@ -282,7 +289,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
     uint32_t const sfa = tmem + 384u, sfb = tmem + 416u;
     uint32_t const desc_hi = (1024u >> 4) | (1u << 14), lbo = (128u >> 4) << 16;     // SBO, descriptor version | LBO
     bool const issuer = lane == 0;
-    uint32_t a_it = 0, ji = 0, tile_ctr = 0;
+    uint32_t a_stage = 0, a_phase = 0, ji = 0, tile_ctr = 0;
     auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
       if (accumulate)
         asm volatile("{\n.reg .b64 da, db;\n.reg .pred p;\nmov.b64 da, {%1, %6};\nmov.b64 db, {%2, %6};\nsetp.eq.b32 p, 0, 0;\n"
@@ -300,9 +307,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         uint32_t const dbase = tmem + odd * 128u;                          // panel column c <-> TMEM column odd * 128 + c
         uint32_t const hfree = odd ? 1u : 0u, hmid = hfree ^ 1u;           // panel halves living in rfree / R1
 #pragma unroll
-        for (int s = 0; s < kSubs; ++s, ++a_it) {
-          uint32_t const st = a_it % kAStages;
-          mbar_wait(full_a(st), (a_it / kAStages) & 1u);
+        for (int s = 0; s < kSubs; ++s) {
+          uint32_t const st = a_stage;
+          mbar_wait(full_a(st), a_phase);
+          if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1u; }
           if (s == 0) mbar_wait(acc_empty(rfree), ((tile_ctr >> 1) & 1u) ^ 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           uint32_t const a_lo = ((sA + st * kStageBytes) >> 4) | lbo, b_lo = ((sB + s * kBSubBytes) >> 4) | lbo;
@@ -367,9 +375,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         for (int w = 0; w < 4; ++w) {
           uint32_t bits = 0;
 #pragma unroll
-          for (int j = 31; j >= 0; --j) {                                   // integer value + 2^23 -> parity in mantissa bit 0
+          for (int j = 0; j < 32; ++j) {                // integer value + 2^23 -> parity in mantissa bit 0 -> funnel-shifted in
             float const f = __uint_as_float(v[32 * w + j]) + 8388608.0f;
-            bits = bits * 2u + (__float_as_uint(f) & 1u);
+            bits = __funnelshift_r(bits, __float_as_uint(f), 1);
           }
           out[w] = bits;
         }
