@@ -9,6 +9,7 @@
 // Shapes: m % 128 == 0, n % 256 == 0, l % 128 == 0; Bt is B transposed (n x l).
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "dev.h"
@@ -178,17 +179,18 @@ struct Tc2Args {
   uint8_t const *imgA[kTcMaxBatch];
   uint8_t const *imgB[kTcMaxBatch];
   long long pitchC;
+  long long *dbg;   // M4RI_B200_TC_DEBUG: per-CTA cycle counters of the MMA warp
   int count, mtiles, nkc, npanels, flags;   // flags: experiment bits (1 skip the parity math)
 };
 
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   long long const t0 = clock64();
-  for (;;) {
+  for (uint32_t spins = 1;; ++spins) {
     uint32_t done;
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000ll) __trap();     // a protocol bug must not hang the box
+    if ((spins & 0xFFFu) == 0 && clock64() - t0 > 4000000000ll) __trap();     // a protocol bug must not hang the box
   }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty_b));
     for (int b = 0; b < 3; ++b) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(acc_full(b)));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(acc_empty(b)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(acc_empty(b)));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -267,6 +269,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         for (int s = 0; s < kSubs; ++s) bulk_g2s(sB + s * kBSubBytes, srcB + (long long)s * kBSubBytes, kBSubBytes, full_b);
         for (int mt = 0; mt < args.mtiles; ++mt) {
           uint8_t const *srcA = args.imgA[p] + ((long long)(mt * args.nkc + kc) * kSubs) * kStageBytes;
+          if (mt + 2 < args.mtiles)       // the ring holds little more than one row tile: warm L2 two tiles ahead
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(srcA + 2ll * args.nkc * kSubs * kStageBytes),
+                         "r"((uint32_t)(kSubs * kStageBytes)) : "memory");
           for (int s = 0; s < kSubs; ++s) {
             uint32_t const st = a_stage;
             mbar_wait(empty_a(st), a_phase ^ 1u);
@@ -290,100 +295,120 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
     uint32_t const desc_hi = (1024u >> 4) | (1u << 14), lbo = (128u >> 4) << 16;     // SBO, descriptor version | LBO
     bool const issuer = lane == 0;
     uint32_t a_stage = 0, a_phase = 0, ji = 0, tile_ctr = 0;
-    auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
-      if (accumulate)
-        asm volatile("{\n.reg .b64 da, db;\n.reg .pred p;\nmov.b64 da, {%1, %6};\nmov.b64 db, {%2, %6};\nsetp.eq.b32 p, 0, 0;\n"
-                     "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], p;\n}"
-                     ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(sfa), "r"(sfb), "r"(desc_hi) : "memory");
-      else
-        asm volatile("{\n.reg .b64 da, db;\n.reg .pred p;\nmov.b64 da, {%1, %6};\nmov.b64 db, {%2, %6};\nsetp.ne.b32 p, 0, 0;\n"
-                     "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], p;\n}"
-                     ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(sfa), "r"(sfb), "r"(desc_hi) : "memory");
+    auto commit_elect = [&](uint32_t bar) {
+      asm volatile("{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+                   "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
+    };
+    long long t_b = 0, t_a = 0, t_free = 0, t_mid = 0, t_begin = clock64();
+    bool const dbg = args.dbg != nullptr;
+#define TC_TIMED(acc, stmt) do { if (dbg) { long long const t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while (0)
+    // four K-steps of one sub-image, issued by one elected lane; the warp runs this convergently
+    auto mma4 = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool first_overwrites, uint32_t commit_bar) {
+      asm volatile(
+          "{\n.reg .pred pe, pt, pf;\n.reg .b64 da, db;\n.reg .b32 al, bl;\n"
+          "elect.sync _|pe, 0xffffffff;\n"
+          "setp.eq.b32 pt, 0, 0;\nsetp.ne.b32 pf, %7, 0;\n"
+          "mov.b64 da, {%1, %6};\nmov.b64 db, {%2, %6};\n"
+          "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], pf;\n"
+          "add.u32 al, %1, 16;\nadd.u32 bl, %2, 16;\nmov.b64 da, {al, %6};\nmov.b64 db, {bl, %6};\n"
+          "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], pt;\n"
+          "add.u32 al, %1, 32;\nadd.u32 bl, %2, 32;\nmov.b64 da, {al, %6};\nmov.b64 db, {bl, %6};\n"
+          "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], pt;\n"
+          "add.u32 al, %1, 48;\nadd.u32 bl, %2, 48;\nmov.b64 da, {al, %6};\nmov.b64 db, {bl, %6};\n"
+          "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], pt;\n"
+          "setp.ne.and.b32 pe, %8, 0, pe;\n"
+          "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n}"
+          ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(sfa), "r"(sfb), "r"(desc_hi), "r"(first_overwrites ? 0u : 1u), "r"(commit_bar)
+          : "memory");
     };
     for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
-      mbar_wait(full_b, ji & 1u);
+      TC_TIMED(t_b, mbar_wait(full_b, ji & 1u));
       for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
         uint32_t const odd = tile_ctr & 1u, rfree = odd ? 2u : 0u;        // this tile: regions {rfree, 1}
         uint32_t const dbase = tmem + odd * 128u;                          // panel column c <-> TMEM column odd * 128 + c
         uint32_t const hfree = odd ? 1u : 0u, hmid = hfree ^ 1u;           // panel halves living in rfree / R1
-#pragma unroll
-        for (int s = 0; s < kSubs; ++s) {
-          uint32_t const st = a_stage;
-          mbar_wait(full_a(st), a_phase);
+        auto next_stage = [&](uint32_t &st) {
+          st = a_stage;
+          TC_TIMED(t_a, mbar_wait(full_a(st), a_phase));
           if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1u; }
-          if (s == 0) mbar_wait(acc_empty(rfree), ((tile_ctr >> 1) & 1u) ^ 1u);
+        };
+        auto a_desc = [&](uint32_t st) { return ((sA + st * kStageBytes) >> 4) | lbo; };
+        auto b_desc = [&](int s) { return ((sB + s * kBSubBytes) >> 4) | lbo; };
+        uint32_t st0, st1, st2;
+        // sub-images 0 and 1 as N = 128 halves: first the half whose region nobody else uses (512 cycles of work), then,
+        // once the previous tile's other half has been drained from R1, the R1 half; sub-images 2 and 3 as N = 256
+        next_stage(st0);
+        TC_TIMED(t_free, mbar_wait(acc_empty(rfree), ((tile_ctr >> 1) & 1u) ^ 1u));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mma4(tmem + rfree * 128u, a_desc(st0), b_desc(0) + hfree * 1024u, idesc128, true, 0u);
+        next_stage(st1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mma4(tmem + rfree * 128u, a_desc(st1), b_desc(1) + hfree * 1024u, idesc128, false, 0u);
+        TC_TIMED(t_mid, mbar_wait(acc_empty(1), (tile_ctr & 1u) ^ 1u));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mma4(tmem + 128u, a_desc(st0), b_desc(0) + hmid * 1024u, idesc128, true, empty_a(st0));
+        mma4(tmem + 128u, a_desc(st1), b_desc(1) + hmid * 1024u, idesc128, false, empty_a(st1));
+#pragma unroll
+        for (int s = 2; s < kSubs; ++s) {
+          next_stage(st2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint32_t const a_lo = ((sA + st * kStageBytes) >> 4) | lbo, b_lo = ((sB + s * kBSubBytes) >> 4) | lbo;
-          if (s == 0) {
-            if (issuer) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) mma(tmem + rfree * 128u, a_lo + 16u * j, b_lo + hfree * 1024u + 16u * j, idesc128, j != 0);
-            }
-            mbar_wait(acc_empty(1), (tile_ctr & 1u) ^ 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (issuer) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) mma(tmem + 128u, a_lo + 16u * j, b_lo + hmid * 1024u + 16u * j, idesc128, j != 0);
-              tc_commit(empty_a(st));
-            }
-          } else if (issuer) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mma(dbase, a_lo + 16u * j, b_lo + 16u * j, idesc256, true);
-            tc_commit(empty_a(st));
-          }
+          mma4(dbase, a_desc(st2), b_desc(s), idesc256, false, empty_a(st2));
         }
-        if (issuer) {
-          tc_commit(acc_full(1));
-          tc_commit(acc_full(rfree));
-        }
+        commit_elect(acc_full(1));
+        commit_elect(acc_full(rfree));
       }
-      if (issuer) tc_commit(empty_b);
+      commit_elect(empty_b);
+    }
+    if (dbg && issuer) {
+      long long *o = args.dbg + 8 * blockIdx.x;
+      o[0] = clock64() - t_begin; o[1] = t_b; o[2] = t_a; o[3] = t_free; o[4] = t_mid; o[5] = tile_ctr;
     }
   } else {                       // ---------------- epilogue: warps 2..9 ----------------
-    // group 0 (warps 2..5) always drains R1 — the region every tile needs again —, group 1 (warps 6..9) R0 / R2 in turn
-    int const q = warp & 3, g = (warp - 2) >> 2;
+    // every warp drains 64 columns of R1 first — the region the next tile is waiting for —, then 64 columns of R0 / R2
+    int const q = warp & 3, hsel = (warp - 2) >> 2;
     uint32_t tile_ctr = 0;
+    auto drain = [&](uint32_t region, uint32_t parity, word *dst) {
+      mbar_wait(acc_full(region), parity);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t const taddr = tmem + ((uint32_t)(q * 32) << 16) + region * 128u + (uint32_t)(hsel * 64 + c * 32);
+        uint32_t *o = v + 32 * c;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]), "=r"(o[9]),
+              "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15]), "=r"(o[16]), "=r"(o[17]), "=r"(o[18]),
+              "=r"(o[19]), "=r"(o[20]), "=r"(o[21]), "=r"(o[22]), "=r"(o[23]), "=r"(o[24]), "=r"(o[25]), "=r"(o[26]), "=r"(o[27]),
+              "=r"(o[28]), "=r"(o[29]), "=r"(o[30]), "=r"(o[31])
+            : "r"(taddr));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(region));
+      if (args.flags & 1) return;
+      uint32_t out[2];
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {                // integer value + 2^23 -> parity in mantissa bit 0 -> funnel-shifted in
+          float const f = __uint_as_float(v[32 * w + j]) + 8388608.0f;
+          bits = __funnelshift_r(bits, __float_as_uint(f), 1);
+        }
+        out[w] = bits;
+      }
+      asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(dst), "l"((unsigned long long)out[0] | ((unsigned long long)out[1] << 32)) : "memory");
+    };
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
       int const p = job / jobs_per_product, np = (job % jobs_per_product) % args.npanels;
       for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
-        uint32_t const odd = tile_ctr & 1u;
-        uint32_t const region = g == 0 ? 1u : (odd ? 2u : 0u);
-        uint32_t const h = g == 0 ? (odd ^ 1u) : odd;                     // the panel half this region holds for this tile
-        mbar_wait(acc_full(region), g == 0 ? (tile_ctr & 1u) : ((tile_ctr >> 1) & 1u));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t v[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t const taddr = tmem + ((uint32_t)(q * 32) << 16) + region * 128u + (uint32_t)(c * 32);
-          uint32_t *o = v + 32 * c;
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]), "=r"(o[9]),
-                "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15]), "=r"(o[16]), "=r"(o[17]), "=r"(o[18]),
-                "=r"(o[19]), "=r"(o[20]), "=r"(o[21]), "=r"(o[22]), "=r"(o[23]), "=r"(o[24]), "=r"(o[25]), "=r"(o[26]), "=r"(o[27]),
-                "=r"(o[28]), "=r"(o[29]), "=r"(o[30]), "=r"(o[31])
-              : "r"(taddr));
-        }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(region));
-        if (args.flags & 1) continue;
-        uint32_t out[4];
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          uint32_t bits = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {                // integer value + 2^23 -> parity in mantissa bit 0 -> funnel-shifted in
-            float const f = __uint_as_float(v[32 * w + j]) + 8388608.0f;
-            bits = __funnelshift_r(bits, __float_as_uint(f), 1);
-          }
-          out[w] = bits;
-        }
-        word *dst = args.C[p] + (long long)(mt * 128 + q * 32 + lane) * args.pitchC + (np * 256 + (int)h * 128) / 64;
-        asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(dst), "l"((unsigned long long)out[0] | ((unsigned long long)out[1] << 32)) : "memory");
-        asm volatile("red.global.xor.b64 [%0], %1;" ::"l"(dst + 1), "l"((unsigned long long)out[2] | ((unsigned long long)out[3] << 32)) : "memory");
+        uint32_t const odd = tile_ctr & 1u, rfree = odd ? 2u : 0u, hfree = odd, hmid = odd ^ 1u;
+        word *row = args.C[p] + (long long)(mt * 128 + q * 32 + lane) * args.pitchC + np * 4 + hsel;
+        drain(1u, tile_ctr & 1u, row + hmid * 2);
+        drain(rfree, (tile_ctr >> 1) & 1u, row + hfree * 2);
       }
     }
   }
@@ -448,8 +473,20 @@ void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) {
   static int const flags = getenv("M4RI_B200_TC_FLAGS") ? atoi(getenv("M4RI_B200_TC_FLAGS")) : 0;
   args.flags = flags;
   int const njobs = args.nkc * args.npanels, grid = njobs < m4rm_num_sms() ? njobs : m4rm_num_sms();
+  static int const debug = getenv("M4RI_B200_TC_DEBUG") ? atoi(getenv("M4RI_B200_TC_DEBUG")) : 0;
+  static long long *dbg = nullptr;
+  if (debug && !dbg) M4B_CUDA(cudaMallocManaged(&dbg, 8 * sizeof(long long) * 1024));
+  args.dbg = debug ? dbg : nullptr;
   tc_leaf2_kernel<<<grid, kTc2Threads, kTc2Smem, s>>>(args);
   M4B_CUDA(cudaGetLastError());
+  if (debug) {
+    M4B_CUDA(cudaStreamSynchronize(s));
+    double sum[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 6; ++k) sum[k] += (double)dbg[8 * b + k];
+    fprintf(stderr, "tc2 MMA warp, mean cycles per CTA: total %.0f | waits: panel %.0f, A stages %.0f, free region %.0f, R1 %.0f | tiles %.0f "
+            "(ideal %.0f cycles of MMA)\n", sum[0] / grid, sum[1] / grid, sum[2] / grid, sum[3] / grid, sum[4] / grid, sum[5] / grid,
+            sum[5] / grid * 2048.0);
+  }
   g_kernel_launches += 5;
 }
 
