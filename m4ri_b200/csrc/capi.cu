@@ -616,7 +616,7 @@ void m4ri_b200_release(void) {
 
 int m4ri_b200_set_leaf_variant(int variant) {
   int const prev = g_leaf_variant;
-  g_leaf_variant = variant >= 0 && variant <= 2 ? variant : -1;    // -1: back to the environment / built-in default
+  g_leaf_variant = variant >= 0 && variant <= 3 ? variant : -1;    // -1: back to the environment / built-in default
   return prev;
 }
 

@@ -461,20 +461,29 @@ int m4rm_num_sms() {   // per device: the library may be pointed at another GPU 
   return sms[dev];
 }
 
-// Leaf selection: M4RI_B200_LEAF=0|1|2 in the environment, or m4ri_b200_set_leaf_variant() at run time.
+// Leaf selection: M4RI_B200_LEAF=0|1|2|3 in the environment, or m4ri_b200_set_leaf_variant() at run time
+// (3: the tensor-core leaf of tc_leaf.cu for C = A*B products it suits, the automatic choice otherwise).
 int g_leaf_variant = -1;
 int g_last_leaf = 0;        // kernel of the most recent leaf launch: 1 = 1024 x 1024-bit tiles, 2 = 4096 x 256-bit tiles
 static int leaf_variant() {
   if (g_leaf_variant < 0) {
     char const *env = getenv("M4RI_B200_LEAF");
-    g_leaf_variant = env && env[0] >= '0' && env[0] <= '2' && !env[1] ? env[0] - '0' : kDefaultLeafVariant;
+    g_leaf_variant = env && env[0] >= '0' && env[0] <= '3' && !env[1] ? env[0] - '0' : kDefaultLeafVariant;
   }
   return g_leaf_variant;
 }
 
 static bool tall_leaf(int m, int l, int n, bool overwrite) {
   int const variant = leaf_variant();
-  return !overwrite && (variant == 2 || (variant == 0 && leaf2_suits(m, l, n)));
+  return !overwrite && (variant == 2 || ((variant == 0 || variant == 3) && leaf2_suits(m, l, n)));
+}
+
+// the tensor-core leaf: C = A*B only (it overwrites C), shapes in its tile units, 16-byte aligned rows of B
+static bool tensor_leaf(int count, DView const *C, DView const *A, DView const *B, bool clear_first) {
+  if (leaf_variant() != 3 || !clear_first || count > 49 || !tc_leaf_suits(A[0].nrows, A[0].ncols, B[0].ncols)) return false;
+  for (int i = 0; i < count; ++i)
+    if ((reinterpret_cast<uintptr_t>(B[i].data) & 15) || (B[i].pitch & 1)) return false;
+  return true;
 }
 
 int m4rm_batch_limit(int m, int l, int n) { return tall_leaf(m, l, n, false) ? 49 : kMaxBatch; }
@@ -497,6 +506,12 @@ static void launch_leaf(int count, DView const *C, DView const *A, DView const *
     ev = &g_prof.pool[g_prof.used++];
     g_prof.bitops += 2.0 * count * A[0].nrows * (double)A[0].ncols * B[0].ncols;
     M4B_CUDA(cudaEventRecord(ev->first, stream));
+  }
+  if (!overwrite && tensor_leaf(count, C, A, B, clear_first)) {
+    g_last_leaf = 3;
+    launch_tc_batch(count, C, A, B, stream);
+    if (ev) M4B_CUDA(cudaEventRecord(ev->second, stream));
+    return;
   }
   bool const tall = tall_leaf(A[0].nrows, A[0].ncols, B[0].ncols, overwrite);
   g_last_leaf = tall ? 2 : 1;

@@ -11,6 +11,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "dev.h"
 
@@ -171,14 +172,14 @@ namespace {
 constexpr int kStageBytes = 16384, kBSubBytes = 32768, kSubs = 4, kAStages = 5;
 constexpr int kPanelBytes = kSubs * kBSubBytes;
 constexpr int kTc2Threads = 320;
-constexpr int kTc2Smem = kPanelBytes + kAStages * kStageBytes + 256 + 1024;
+constexpr int kTc2Smem = kPanelBytes + kAStages * kStageBytes + 256 + 1024;   // + barriers + alignment slack
 constexpr int kTcMaxBatch = 49;
 
 struct Tc2Args {
   word *C[kTcMaxBatch];
   uint8_t const *imgA[kTcMaxBatch];
   uint8_t const *imgB[kTcMaxBatch];
-  long long pitchC;
+  int pitchC[kTcMaxBatch];
   long long *dbg;   // M4RI_B200_TC_DEBUG: per-CTA cycle counters of the MMA warp
   int count, mtiles, nkc, npanels, flags;   // flags: experiment bits (1 skip the parity math)
 };
@@ -208,20 +209,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, void const *src, uint32_t
                "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 
 __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_constant__ Tc2Args args) {
   extern __shared__ uint8_t smem_raw[];
   uint32_t const base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint32_t const sB = base, sA = base + kPanelBytes, bars = sA + kAStages * kStageBytes;
-  // barriers (8 bytes each): full_a[5] empty_a[5] full_b empty_b acc_full[3] acc_empty[3]
+  // barriers (8 bytes each): full_a[5] empty_a[5] full_b[4] empty_b[4] acc_full[3] acc_empty[3]
   auto full_a = [&](int s) { return bars + 8u * s; };
   auto empty_a = [&](int s) { return bars + 8u * (kAStages + s); };
-  uint32_t const full_b = bars + 8u * (2 * kAStages), empty_b = full_b + 8u;
-  auto acc_full = [&](int b) { return empty_b + 8u + 8u * b; };
-  auto acc_empty = [&](int b) { return empty_b + 8u + 8u * (3 + b); };
+  auto full_b = [&](int s) { return bars + 8u * (2 * kAStages + s); };
+  auto empty_b = [&](int s) { return bars + 8u * (2 * kAStages + kSubs + s); };
+  auto acc_full = [&](int b) { return bars + 8u * (2 * kAStages + 2 * kSubs + b); };
+  auto acc_empty = [&](int b) { return bars + 8u * (2 * kAStages + 2 * kSubs + 3 + b); };
   __shared__ uint32_t tmem_slot;
   int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -229,8 +228,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a(s)));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty_a(s)));
     }
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_b));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty_b));
+    for (int s = 0; s < kSubs; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_b(s)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty_b(s)));
+    }
     for (int b = 0; b < 3; ++b) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(acc_full(b)));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(acc_empty(b)));
@@ -263,10 +264,21 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
       uint32_t a_stage = 0, a_phase = 0, ji = 0;
       for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
         int const p = job / jobs_per_product, rem = job % jobs_per_product, kc = rem / args.npanels, np = rem % args.npanels;
-        mbar_wait(empty_b, (ji & 1u) ^ 1u);
-        mbar_expect_tx(full_b, kPanelBytes);
         uint8_t const *srcB = args.imgB[p] + ((long long)(np * args.nkc + kc) * kSubs) * kBSubBytes;
-        for (int s = 0; s < kSubs; ++s) bulk_g2s(sB + s * kBSubBytes, srcB + (long long)s * kBSubBytes, kBSubBytes, full_b);
+        for (int s = 0; s < kSubs; ++s) {       // each sub-image of the panel as soon as the previous job has let go of it
+          mbar_wait(empty_b(s), (ji & 1u) ^ 1u);
+          mbar_expect_tx(full_b(s), kBSubBytes);
+          bulk_g2s(sB + s * kBSubBytes, srcB + (long long)s * kBSubBytes, kBSubBytes, full_b(s));
+        }
+        {                                        // ... and the next job's panel into L2 meanwhile
+          int const nj = job + gridDim.x;
+          if (nj < njobs) {
+            int const p2 = nj / jobs_per_product, r2 = nj % jobs_per_product, kc2 = r2 / args.npanels, np2 = r2 % args.npanels;
+            uint8_t const *nb = args.imgB[p2] + ((long long)(np2 * args.nkc + kc2) * kSubs) * kBSubBytes;
+            for (int s = 0; s < kSubs; ++s)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nb + (long long)s * kBSubBytes), "r"((uint32_t)kBSubBytes) : "memory");
+          }
+        }
         for (int mt = 0; mt < args.mtiles; ++mt) {
           uint8_t const *srcA = args.imgA[p] + ((long long)(mt * args.nkc + kc) * kSubs) * kStageBytes;
           if (mt + 2 < args.mtiles)       // the ring holds little more than one row tile: warm L2 two tiles ahead
@@ -322,7 +334,6 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
           : "memory");
     };
     for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
-      TC_TIMED(t_b, mbar_wait(full_b, ji & 1u));
       for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
         uint32_t const odd = tile_ctr & 1u, rfree = odd ? 2u : 0u;        // this tile: regions {rfree, 1}
         uint32_t const dbase = tmem + odd * 128u;                          // panel column c <-> TMEM column odd * 128 + c
@@ -337,27 +348,33 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         uint32_t st0, st1, st2;
         // sub-images 0 and 1 as N = 128 halves: first the half whose region nobody else uses (512 cycles of work), then,
         // once the previous tile's other half has been drained from R1, the R1 half; sub-images 2 and 3 as N = 256
+        bool const first = mt == 0, last = mt + 1 == args.mtiles;    // of this job: the panel arrives / is let go piecewise
         next_stage(st0);
+        if (first) TC_TIMED(t_b, mbar_wait(full_b(0), ji & 1u));
         TC_TIMED(t_free, mbar_wait(acc_empty(rfree), ((tile_ctr >> 1) & 1u) ^ 1u));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         mma4(tmem + rfree * 128u, a_desc(st0), b_desc(0) + hfree * 1024u, idesc128, true, 0u);
         next_stage(st1);
+        if (first) TC_TIMED(t_b, mbar_wait(full_b(1), ji & 1u));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         mma4(tmem + rfree * 128u, a_desc(st1), b_desc(1) + hfree * 1024u, idesc128, false, 0u);
         TC_TIMED(t_mid, mbar_wait(acc_empty(1), (tile_ctr & 1u) ^ 1u));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         mma4(tmem + 128u, a_desc(st0), b_desc(0) + hmid * 1024u, idesc128, true, empty_a(st0));
+        if (last) commit_elect(empty_b(0));
         mma4(tmem + 128u, a_desc(st1), b_desc(1) + hmid * 1024u, idesc128, false, empty_a(st1));
+        if (last) commit_elect(empty_b(1));
 #pragma unroll
         for (int s = 2; s < kSubs; ++s) {
           next_stage(st2);
+          if (first) TC_TIMED(t_b, mbar_wait(full_b(s), ji & 1u));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           mma4(dbase, a_desc(st2), b_desc(s), idesc256, false, empty_a(st2));
+          if (last) commit_elect(empty_b(s));
         }
         commit_elect(acc_full(1));
         commit_elect(acc_full(rfree));
       }
-      commit_elect(empty_b);
     }
     if (dbg && issuer) {
       long long *o = args.dbg + 8 * blockIdx.x;
@@ -406,7 +423,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
       int const p = job / jobs_per_product, np = (job % jobs_per_product) % args.npanels;
       for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
         uint32_t const odd = tile_ctr & 1u, rfree = odd ? 2u : 0u, hfree = odd, hmid = odd ^ 1u;
-        word *row = args.C[p] + (long long)(mt * 128 + q * 32 + lane) * args.pitchC + np * 4 + hsel;
+        word *row = args.C[p] + (long long)(mt * 128 + q * 32 + lane) * args.pitchC[p] + np * 4 + hsel;
         drain(1u, tile_ctr & 1u, row + hmid * 2);
         drain(rfree, (tile_ctr >> 1) & 1u, row + hfree * 2);
       }
@@ -417,62 +434,125 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-// bits of M (rows x K) -> the tiled e2m1 image; one thread per 16-byte core-matrix row (32 elements)
-__global__ void tc_expand_kernel(uint4 *img, word const *M, long long pitch, int R, int nkc, long long total) {
+struct TcPrepArgs {
+  word const *A[kTcMaxBatch];
+  word const *B[kTcMaxBatch];
+  word *C[kTcMaxBatch];
+  uint8_t *imgA[kTcMaxBatch];
+  uint8_t *imgB[kTcMaxBatch];
+  int pitchA[kTcMaxBatch], pitchB[kTcMaxBatch], pitchC[kTcMaxBatch];
+  int m, l, n, nkc;
+};
+
+// A operands: bits of A (m x l) -> the tiled e2m1 image, one thread per 16-byte core-matrix row (32 elements);
+// blockIdx.y = product.  The same threads clear C (the main kernel XORs partial sums into it).
+__global__ void __launch_bounds__(256) tc_expand_a_kernel(const __grid_constant__ TcPrepArgs a) {
+  int const p = blockIdx.y;
+  long long const total = (long long)a.m * a.l / 32;
   long long const o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= total) return;
-  long long const sub = o / (R * 8);
-  int const within = (int)(o % (R * 8)), rg = within / 64, kg = (within / 8) % 8, r8 = within % 8;
-  int const s = (int)(sub % kSubs), kc = (int)((sub / kSubs) % nkc);
-  long long const tile = sub / ((long long)kSubs * nkc);
-  long long const row = tile * R + rg * 8 + r8;
-  uint32_t const bits = reinterpret_cast<uint32_t const *>(M + row * pitch)[kc * 32 + s * 8 + kg];
-  img[o] = make_uint4(expand8(bits), expand8(bits >> 8), expand8(bits >> 16), expand8(bits >> 24));
+  if (o < total) {
+    long long const sub = o / (128 * 8);
+    int const within = (int)(o % (128 * 8)), rg = within / 64, kg = (within / 8) % 8, r8 = within % 8;
+    int const s = (int)(sub % kSubs), kc = (int)((sub / kSubs) % a.nkc);
+    long long const tile = sub / ((long long)kSubs * a.nkc);
+    long long const row = tile * 128 + rg * 8 + r8;
+    uint32_t const bits = reinterpret_cast<uint32_t const *>(a.A[p] + row * a.pitchA[p])[kc * 32 + s * 8 + kg];
+    reinterpret_cast<uint4 *>(a.imgA[p])[o] = make_uint4(expand8(bits), expand8(bits >> 8), expand8(bits >> 16), expand8(bits >> 24));
+  }
+  long long const cwords = (long long)a.m * (a.n / 64);            // C: m rows of n / 64 words
+  for (long long w = o; w < cwords; w += (long long)gridDim.x * blockDim.x) a.C[p][(w / (a.n / 64)) * a.pitchC[p] + w % (a.n / 64)] = 0;
 }
 
-struct TcScratch { uint8_t *imgA = nullptr, *imgB = nullptr; word *bt = nullptr; size_t a = 0, b = 0, t = 0; int device = -1; };
-TcScratch g_tc;
+// lane i holds row i of a 32 x 32 bit block (column j in bit j); returns column `lane` as a row
+__device__ __forceinline__ uint32_t tc_transpose32(uint32_t x, int lane) {
+  uint32_t m = 0x0000FFFFu;
+#pragma unroll
+  for (int j = 16; j; j >>= 1) {
+    uint32_t const y = __shfl_xor_sync(0xffffffffu, x, j);
+    if (lane & j) x = (x & (m << j)) | ((y >> j) & m);
+    else          x = (x & m) | ((y & m) << j);
+    m ^= m << (j >> 1);
+  }
+  return x;
+}
+
+// B operands: the image rows are the COLUMNS of B.  One CTA = one 32 KB sub-image (256 columns x 256 K); warp w owns the
+// K rows 32 w .. 32 w + 31 of it: a lane reads 32 bytes of its row (one sector), eight 32 x 32 bit blocks are transposed
+// in registers, and lane j ends up with 32 K-bits of column j -> one 16-byte core-matrix row of the image.
+__global__ void __launch_bounds__(256) tc_expand_bt_kernel(const __grid_constant__ TcPrepArgs a) {
+  int const p = blockIdx.z, np = blockIdx.x, ks = blockIdx.y;        // ks = kc * 4 + s: K rows 256 ks ..
+  int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int const kc = ks / kSubs, s = ks % kSubs;
+  uint4 const *src = reinterpret_cast<uint4 const *>(a.B[p] + (long long)(ks * 256 + warp * 32 + lane) * a.pitchB[p] + np * 4);
+  uint4 const lo = src[0], hi = src[1];
+  uint32_t const x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint8_t *sub = a.imgB[p] + ((long long)(np * a.nkc + kc) * kSubs + s) * kBSubBytes;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    uint32_t const bits = tc_transpose32(x[nb], lane);      // K bits 32 warp .. of column 32 nb + lane
+    int const n = nb * 32 + lane;
+    *reinterpret_cast<uint4 *>(sub + (n / 8) * 1024 + warp * 128 + (n % 8) * 16) =
+        make_uint4(expand8(bits), expand8(bits >> 8), expand8(bits >> 16), expand8(bits >> 24));
+  }
+}
+
+struct TcScratch { uint8_t *a = nullptr, *b = nullptr; size_t bytes_a = 0, bytes_b = 0; };
+TcScratch g_tc[16];
+std::mutex g_tc_mu;
 
 }  // namespace
 
-// C = A * B (C is overwritten), experimental B-stationary tensor-core form; m % 128 == 0, l % 1024 == 0, n % 256 == 0
-void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) {
-  int const m = A.nrows, l = A.ncols, n = B.ncols;
-  if (m % 128 || l % 1024 || n % 256 || B.nrows != l || C.nrows != m || C.ncols != n)
-    die("m4ri_b200_dmul_tc2: needs m %% 128 == 0, l %% 1024 == 0, n %% 256 == 0\n");
-  size_t const need_a = (size_t)m * l / 2, need_b = (size_t)n * l / 2, need_t = (size_t)n * (l / 64) * sizeof(word);
+bool tc_leaf_suits(int m, int l, int n) { return m >= 128 && m % 128 == 0 && l >= 1024 && l % 1024 == 0 && n >= 256 && n % 256 == 0; }
+
+// C[i] = A[i] * B[i] for up to 49 products of one shape on the tensor cores (C is overwritten)
+void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t s) {
+  int const m = A[0].nrows, l = A[0].ncols, n = B[0].ncols;
+  if (count < 1 || count > kTcMaxBatch || !tc_leaf_suits(m, l, n))
+    die("m4ri_b200: tensor-core leaf needs <= 49 products with m %% 128 == 0, l %% 1024 == 0, n %% 256 == 0\n");
+  size_t const each_a = (size_t)m * l / 2, each_b = (size_t)n * l / 2;
   int dev = 0;
   M4B_CUDA(cudaGetDevice(&dev));
-  if (g_tc.device != dev || g_tc.a < need_a || g_tc.b < need_b || g_tc.t < need_t) {
-    M4B_CUDA(cudaDeviceSynchronize());
-    if (g_tc.imgA) cudaFree(g_tc.imgA);
-    if (g_tc.imgB) cudaFree(g_tc.imgB);
-    if (g_tc.bt) cudaFree(g_tc.bt);
-    M4B_CUDA(cudaMalloc(&g_tc.imgA, need_a));
-    M4B_CUDA(cudaMalloc(&g_tc.imgB, need_b));
-    M4B_CUDA(cudaMalloc(&g_tc.bt, need_t));
-    g_tc.a = need_a; g_tc.b = need_b; g_tc.t = need_t; g_tc.device = dev;
+  TcScratch *sc;
+  {
+    std::lock_guard<std::mutex> lock(g_tc_mu);
+    sc = &g_tc[dev & 15];
+    if (sc->bytes_a < each_a * count || sc->bytes_b < each_b * count) {
+      M4B_CUDA(cudaDeviceSynchronize());
+      if (sc->a) cudaFree(sc->a);
+      if (sc->b) cudaFree(sc->b);
+      M4B_CUDA(cudaMalloc(&sc->a, each_a * count));
+      M4B_CUDA(cudaMalloc(&sc->b, each_b * count));
+      sc->bytes_a = each_a * count; sc->bytes_b = each_b * count;
+    }
   }
-  DView Bt{g_tc.bt, (long long)(l / 64), n, l};
-  int const nkc = l / 1024;
-  long long const ta = (long long)need_a / 16, tb = (long long)need_b / 16;
+  TcPrepArgs prep{};
+  Tc2Args args{};
+  for (int i = 0; i < count; ++i) {
+    if (A[i].nrows != m || A[i].ncols != l || B[i].nrows != l || B[i].ncols != n || C[i].nrows != m || C[i].ncols != n)
+      die("m4ri_b200: tensor-core leaf batch needs identical shapes\n");
+    prep.pitchA[i] = (int)A[i].pitch; prep.pitchB[i] = (int)B[i].pitch; prep.pitchC[i] = (int)C[i].pitch;
+    args.pitchC[i] = (int)C[i].pitch;
+    prep.A[i] = A[i].data; prep.B[i] = B[i].data; prep.C[i] = C[i].data;
+    prep.imgA[i] = sc->a + each_a * i; prep.imgB[i] = sc->b + each_b * i;
+    args.C[i] = C[i].data; args.imgA[i] = prep.imgA[i]; args.imgB[i] = prep.imgB[i];
+  }
+  prep.m = m; prep.l = l; prep.n = n; prep.nkc = l / 1024;
   static int const reuse = getenv("M4RI_B200_TC_REUSE") ? atoi(getenv("M4RI_B200_TC_REUSE")) : 0;   // timing knob: keep the images
   static word const *last_a = nullptr, *last_b = nullptr;
-  if (!(reuse && last_a == A.data && last_b == B.data)) {
-    launch_transpose(Bt, B, s);
-    tc_expand_kernel<<<(unsigned)((ta + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(g_tc.imgA), A.data, A.pitch, 128, nkc, ta);
-    tc_expand_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(g_tc.imgB), Bt.data, Bt.pitch, 256, nkc, tb);
-    last_a = A.data; last_b = B.data;
+  long long const units = (long long)m * l / 32;
+  if (reuse && count == 1 && last_a == A[0].data && last_b == B[0].data) {
+    M4B_CUDA(cudaMemset2DAsync(C[0].data, C[0].pitch * sizeof(word), 0, (size_t)(n / 64) * sizeof(word), m, s));
+  } else {
+    tc_expand_a_kernel<<<dim3((unsigned)((units + 255) / 256), count), 256, 0, s>>>(prep);
+    tc_expand_bt_kernel<<<dim3(n / 256, l / 256, count), 256, 0, s>>>(prep);
+    last_a = A[0].data; last_b = B[0].data;
   }
-  M4B_CUDA(cudaMemset2DAsync(C.data, C.pitch * sizeof(word), 0, (size_t)(n / 64) * sizeof(word), m, s));
-  Tc2Args args{};
-  args.C[0] = C.data; args.imgA[0] = g_tc.imgA; args.imgB[0] = g_tc.imgB;
-  args.pitchC = C.pitch; args.count = 1; args.mtiles = m / 128; args.nkc = nkc; args.npanels = n / 256;
-  static bool attr = false;
-  if (!attr) { M4B_CUDA(cudaFuncSetAttribute(tc_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem)); attr = true; }
+  args.count = count; args.mtiles = m / 128; args.nkc = l / 1024; args.npanels = n / 256;
+  static bool attr[16] = {};
+  if (!attr[dev & 15]) { M4B_CUDA(cudaFuncSetAttribute(tc_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem)); attr[dev & 15] = true; }
   static int const flags = getenv("M4RI_B200_TC_FLAGS") ? atoi(getenv("M4RI_B200_TC_FLAGS")) : 0;
   args.flags = flags;
-  int const njobs = args.nkc * args.npanels, grid = njobs < m4rm_num_sms() ? njobs : m4rm_num_sms();
+  int const njobs = count * args.nkc * args.npanels, grid = njobs < m4rm_num_sms() ? njobs : m4rm_num_sms();
   static int const debug = getenv("M4RI_B200_TC_DEBUG") ? atoi(getenv("M4RI_B200_TC_DEBUG")) : 0;
   static long long *dbg = nullptr;
   if (debug && !dbg) M4B_CUDA(cudaMallocManaged(&dbg, 8 * sizeof(long long) * 1024));
@@ -487,7 +567,9 @@ void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) {
             "(ideal %.0f cycles of MMA)\n", sum[0] / grid, sum[1] / grid, sum[2] / grid, sum[3] / grid, sum[4] / grid, sum[5] / grid,
             sum[5] / grid * 2048.0);
   }
-  g_kernel_launches += 5;
+  g_kernel_launches += 3;
 }
+
+void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) { launch_tc_batch(1, &C, &A, &B, s); }
 
 }  // namespace m4b
