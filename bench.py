@@ -878,6 +878,27 @@ def run_own_arm(args):
             traffic = json.load(f).get(("leaf2:" if leaf_variant == 2 else "") + "x".join(str(d) for d in leaf_dims))
         if traffic is not None:
             traffic *= products_per_launch
+    tensor_roofline = None
+    if leaf_variant == 3:
+        # The tensor-core leaf (tc_leaf.cu): every GF(2) multiply-add is one e2m1 multiply-add of tcgen05.mma kind::mxf4,
+        # so the leaf's bit-ops ARE its tensor flops.  Peak: 4 x the measured dense bf16 figure of MEASURED_PEAKS.json
+        # (e2m1 block-scaled runs at four times the bf16 rate; the burst figure, as the leaf is timed launch by launch);
+        # beside it the mxf4 instruction-issue ceiling measured by tools/tc/tc05_probe.cu on this pool (8.91e15).
+        bf16_burst, bf16_sust = 1590.0, None
+        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(ppath):
+            with open(ppath) as f:
+                pk = json.load(f)
+            bf16_burst, bf16_sust = float(pk.get("bf16_tflops", bf16_burst)), pk.get("bf16_tflops_sustained")
+        peak_tf = 4.0 * bf16_burst
+        tensor_roofline = {
+            "kernel": "tc_leaf2_kernel", "bound": "tensor", "unit": "TFLOP/s", "achieved": leaf_rate / 1e12, "peak": peak_tf,
+            "frac": leaf_rate / 1e12 / peak_tf,
+            "peak_source": f"4 x dense bf16 {bf16_burst:.0f} TFLOP/s ({peak_src}; e2m1 runs at 4x the bf16 rate)",
+            "frac_of_sustained_peak": (leaf_rate / 1e12 / (4.0 * float(bf16_sust))) if bf16_sust else None,
+            "frac_of_mxf4_issue_ceiling": leaf_rate / 8.912e15,
+            "includes": "operand expansion to e2m1 (two streaming kernels per launch) and the parity epilogue",
+        }
     roofline = {
         "kernel": "m4rm_leaf2_kernel" if leaf_variant == 2 else "m4rm_streamk_kernel", "bound": "smem", "unit": "GB/s",
         "algorithmic_smem_bytes_per_bitop": smem_bytes_per_bitop,
@@ -893,6 +914,13 @@ def run_own_arm(args):
                 "peak": hbm_peak, "frac": (hbm_bytes / (leaf_avg_ms * 1e-3) / 1e9) / hbm_peak if leaf_avg_ms else 0.0,
                 "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src},
     }
+
+    if tensor_roofline is not None:
+        for k in ("traffic", "leaf_launches", "leaf_avg_ms", "leaf_dims", "products_per_launch", "leaf_bitops_per_s",
+                  "leaf_share_of_step", "hbm"):
+            tensor_roofline[k] = roofline[k]
+        tensor_roofline["traffic"] = None
+        roofline = tensor_roofline
 
     # ---- the HBM-bound kernel of the path: the device _mzd_add (C = A ^ B) on square operands ----------
     add_roofline = None
@@ -926,6 +954,9 @@ def run_own_arm(args):
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "dims": [m, l, n],
                    "cutoff": cutoff or lib.m4ri_b200_get_default_cutoff(), "path": path,
+                   "leaf": {1: "M4RM, 1024 x 1024-bit tiles (CUDA cores)", 2: "M4RM, 4096 x 256-bit tall tiles (CUDA cores)",
+                            3: "tcgen05.mma kind::mxf4 on e2m1-expanded bits, f32 accumulators in TMEM, parity epilogue "
+                               "(exact: sums < 2^24)"}.get(leaf_variant, str(leaf_variant)),
                    "parallelism": (f"row-block x{world}" if pc == 1 else f"C blocks {pr} x {pc} (row-blocks x column-blocks)") +
                                   ("" if world == 1 else ", NCCL all-gather of B per step" if pc == 1 else
                                    f", NCCL all-gather of B's column block inside each column group ({pr} ranks) per step"),

@@ -35,7 +35,8 @@ static_assert(offsetof(mzd_t, nrows) == 0 && offsetof(mzd_t, ncols) == 4 && offs
 namespace {
 
 constexpr uint8_t kFlagExcess = 0x2, kFlagWindow = 0x4;
-constexpr int kBuiltinCutoff = 4096;   // device Strassen leaf size (4096-row leaves, 49 per launch); tuned on B200, see DESIGN.md
+constexpr int kBuiltinCutoff = 8192;   // device Strassen leaf size with the tensor-core leaf (49 per launch); tuned on B200, see DESIGN.md
+constexpr int kBuiltinCutoffM4rm = 4096;   // ... when M4RI_B200_LEAF pins the M4RM leaves (4096-row tall tiles)
 
 struct Ctx {
   bool         ready = false;
@@ -76,7 +77,9 @@ Ctx &ctx() {
     if (getenv("M4RI_B200_REPORT")) atexit(report_at_exit);
     if (!g.default_cutoff) {
       char const *env = getenv("M4RI_B200_CUTOFF");
-      g.default_cutoff = env && atoi(env) > 0 ? atoi(env) : kBuiltinCutoff;
+      char const *leaf = getenv("M4RI_B200_LEAF");
+      bool const m4rm_only = leaf && (leaf[0] == '1' || leaf[0] == '2') && !leaf[1];
+      g.default_cutoff = env && atoi(env) > 0 ? atoi(env) : (m4rm_only ? kBuiltinCutoffM4rm : kBuiltinCutoff);
     }
     g.ready = true;
   }
@@ -608,6 +611,7 @@ int  m4ri_b200_get_default_cutoff(void) { return g.default_cutoff ? g.default_cu
 void m4ri_b200_release(void) {
   M4B_LOCKED;
   multi_release();
+  tc_scratch_release();
   if (!g.ready) return;
   cudaStreamSynchronize(g.stream);
   g.ws.destroy();

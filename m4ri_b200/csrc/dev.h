@@ -129,6 +129,7 @@ size_t echelon_workspace_bytes(int m, int n, int64_t pitch_words = 0);   // pitc
 void launch_tc_leaf_simple(DView C, DView A, DView Bt, bool accumulate, cudaStream_t s);
 void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s);        // pipelined B-stationary form, C = A * B
 bool tc_leaf_suits(int m, int l, int n);
+void tc_scratch_release();
 void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t s);   // <= 49 products, C overwritten
 
 // ---- PLE decomposition (ple.cu) ----------------------------------------------------------------

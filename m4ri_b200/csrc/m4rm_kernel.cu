@@ -462,7 +462,9 @@ int m4rm_num_sms() {   // per device: the library may be pointed at another GPU 
 }
 
 // Leaf selection: M4RI_B200_LEAF=0|1|2|3 in the environment, or m4ri_b200_set_leaf_variant() at run time
-// (3: the tensor-core leaf of tc_leaf.cu for C = A*B products it suits, the automatic choice otherwise).
+// 0 (default): the tensor-core leaf of tc_leaf.cu for the C = A*B products it suits (every dimension in its tile units:
+// the Strassen leaves of large products), else the tall-tile M4RM leaf where that suits, else the 1024-row M4RM leaf;
+// 1 / 2: M4RM only (1024-row tiles / tall tiles for every shape); 3: same as 0.
 int g_leaf_variant = -1;
 int g_last_leaf = 0;        // kernel of the most recent leaf launch: 1 = 1024 x 1024-bit tiles, 2 = 4096 x 256-bit tiles
 static int leaf_variant() {
@@ -480,7 +482,8 @@ static bool tall_leaf(int m, int l, int n, bool overwrite) {
 
 // the tensor-core leaf: C = A*B only (it overwrites C), shapes in its tile units, 16-byte aligned rows of B
 static bool tensor_leaf(int count, DView const *C, DView const *A, DView const *B, bool clear_first) {
-  if (leaf_variant() != 3 || !clear_first || count > 49 || !tc_leaf_suits(A[0].nrows, A[0].ncols, B[0].ncols)) return false;
+  int const variant = leaf_variant();
+  if ((variant != 0 && variant != 3) || !clear_first || count > 49 || !tc_leaf_suits(A[0].nrows, A[0].ncols, B[0].ncols)) return false;
   for (int i = 0; i < count; ++i)
     if ((reinterpret_cast<uintptr_t>(B[i].data) & 15) || (B[i].pitch & 1)) return false;
   return true;

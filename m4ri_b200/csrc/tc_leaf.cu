@@ -572,4 +572,20 @@ void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, 
 
 void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) { launch_tc_batch(1, &C, &A, &B, s); }
 
+// frees the operand-image scratch of every device (m4ri_b200_release)
+void tc_scratch_release() {
+  std::lock_guard<std::mutex> lock(g_tc_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < 16; ++d) {
+    if (!g_tc[d].a && !g_tc[d].b) continue;
+    cudaSetDevice(d);
+    cudaDeviceSynchronize();
+    cudaFree(g_tc[d].a);
+    cudaFree(g_tc[d].b);
+    g_tc[d] = TcScratch{};
+  }
+  cudaSetDevice(cur);
+}
+
 }  // namespace m4b
