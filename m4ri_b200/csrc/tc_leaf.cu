@@ -180,7 +180,6 @@ struct Tc2Args {
   uint8_t const *imgA[kTcMaxBatch];
   uint8_t const *imgB[kTcMaxBatch];
   int pitchC[kTcMaxBatch];
-  long long *dbg;   // M4RI_B200_TC_DEBUG: per-CTA cycle counters of the MMA warp
   int count, mtiles, nkc, npanels, flags;   // flags: experiment bits (1 skip the parity math)
 };
 
@@ -305,15 +304,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
     uint32_t const idesc256 = (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | (1u << 23) | ((uint32_t)(128 >> 4) << 24);
     uint32_t const sfa = tmem + 384u, sfb = tmem + 416u;
     uint32_t const desc_hi = (1024u >> 4) | (1u << 14), lbo = (128u >> 4) << 16;     // SBO, descriptor version | LBO
-    bool const issuer = lane == 0;
     uint32_t a_stage = 0, a_phase = 0, ji = 0, tile_ctr = 0;
     auto commit_elect = [&](uint32_t bar) {
       asm volatile("{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
                    "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
     };
-    long long t_b = 0, t_a = 0, t_free = 0, t_mid = 0, t_begin = clock64();
-    bool const dbg = args.dbg != nullptr;
-#define TC_TIMED(acc, stmt) do { if (dbg) { long long const t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while (0)
     // four K-steps of one sub-image, issued by one elected lane; the warp runs this convergently
     auto mma4 = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool first_overwrites, uint32_t commit_bar) {
       asm volatile(
@@ -340,7 +335,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         uint32_t const hfree = odd ? 1u : 0u, hmid = hfree ^ 1u;           // panel halves living in rfree / R1
         auto next_stage = [&](uint32_t &st) {
           st = a_stage;
-          TC_TIMED(t_a, mbar_wait(full_a(st), a_phase));
+          mbar_wait(full_a(st), a_phase);
           if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1u; }
         };
         auto a_desc = [&](uint32_t st) { return ((sA + st * kStageBytes) >> 4) | lbo; };
@@ -350,15 +345,15 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         // once the previous tile's other half has been drained from R1, the R1 half; sub-images 2 and 3 as N = 256
         bool const first = mt == 0, last = mt + 1 == args.mtiles;    // of this job: the panel arrives / is let go piecewise
         next_stage(st0);
-        if (first) TC_TIMED(t_b, mbar_wait(full_b(0), ji & 1u));
-        TC_TIMED(t_free, mbar_wait(acc_empty(rfree), ((tile_ctr >> 1) & 1u) ^ 1u));
+        if (first) mbar_wait(full_b(0), ji & 1u);
+        mbar_wait(acc_empty(rfree), ((tile_ctr >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         mma4(tmem + rfree * 128u, a_desc(st0), b_desc(0) + hfree * 1024u, idesc128, true, 0u);
         next_stage(st1);
-        if (first) TC_TIMED(t_b, mbar_wait(full_b(1), ji & 1u));
+        if (first) mbar_wait(full_b(1), ji & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         mma4(tmem + rfree * 128u, a_desc(st1), b_desc(1) + hfree * 1024u, idesc128, false, 0u);
-        TC_TIMED(t_mid, mbar_wait(acc_empty(1), (tile_ctr & 1u) ^ 1u));
+        mbar_wait(acc_empty(1), (tile_ctr & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         mma4(tmem + 128u, a_desc(st0), b_desc(0) + hmid * 1024u, idesc128, true, empty_a(st0));
         if (last) commit_elect(empty_b(0));
@@ -367,7 +362,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
 #pragma unroll
         for (int s = 2; s < kSubs; ++s) {
           next_stage(st2);
-          if (first) TC_TIMED(t_b, mbar_wait(full_b(s), ji & 1u));
+          if (first) mbar_wait(full_b(s), ji & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           mma4(dbase, a_desc(st2), b_desc(s), idesc256, false, empty_a(st2));
           if (last) commit_elect(empty_b(s));
@@ -375,10 +370,6 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
         commit_elect(acc_full(1));
         commit_elect(acc_full(rfree));
       }
-    }
-    if (dbg && issuer) {
-      long long *o = args.dbg + 8 * blockIdx.x;
-      o[0] = clock64() - t_begin; o[1] = t_b; o[2] = t_a; o[3] = t_free; o[4] = t_mid; o[5] = tile_ctr;
     }
   } else {                       // ---------------- epilogue: warps 2..9 ----------------
     // every warp drains 64 columns of R1 first — the region the next tile is waiting for —, then 64 columns of R0 / R2
@@ -553,20 +544,8 @@ void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, 
   static int const flags = getenv("M4RI_B200_TC_FLAGS") ? atoi(getenv("M4RI_B200_TC_FLAGS")) : 0;
   args.flags = flags;
   int const njobs = count * args.nkc * args.npanels, grid = njobs < m4rm_num_sms() ? njobs : m4rm_num_sms();
-  static int const debug = getenv("M4RI_B200_TC_DEBUG") ? atoi(getenv("M4RI_B200_TC_DEBUG")) : 0;
-  static long long *dbg = nullptr;
-  if (debug && !dbg) M4B_CUDA(cudaMallocManaged(&dbg, 8 * sizeof(long long) * 1024));
-  args.dbg = debug ? dbg : nullptr;
   tc_leaf2_kernel<<<grid, kTc2Threads, kTc2Smem, s>>>(args);
   M4B_CUDA(cudaGetLastError());
-  if (debug) {
-    M4B_CUDA(cudaStreamSynchronize(s));
-    double sum[6] = {0, 0, 0, 0, 0, 0};
-    for (int b = 0; b < grid; ++b) for (int k = 0; k < 6; ++k) sum[k] += (double)dbg[8 * b + k];
-    fprintf(stderr, "tc2 MMA warp, mean cycles per CTA: total %.0f | waits: panel %.0f, A stages %.0f, free region %.0f, R1 %.0f | tiles %.0f "
-            "(ideal %.0f cycles of MMA)\n", sum[0] / grid, sum[1] / grid, sum[2] / grid, sum[3] / grid, sum[4] / grid, sum[5] / grid,
-            sum[5] / grid * 2048.0);
-  }
   g_kernel_launches += 3;
 }
 
