@@ -161,7 +161,7 @@ void launch_tc_leaf_simple(DView C, DView A, DView Bt, bool accumulate, cudaStre
 //   A image:  [row tile of 128][K chunk of 1024][sub 0..3] x 16 KB   (sub-image = 128 rows x 256 elements)
 //   B image:  [column panel of 256][K chunk][sub 0..3]     x 32 KB   (rows = columns of B, from B^T)
 // A job = (product, K chunk, column panel): the 128 KB panel chunk stays in shared memory while EVERY row tile of A
-// streams past it through a ring of 16 KB stages (4 KB of L2 traffic per 128-cycle MMA pair = 31 B/clk/SM, under the L2
+// streams past it through a ring of three 32 KB stages (two sub-images each) (4 KB of L2 traffic per 128-cycle MMA pair = 31 B/clk/SM, under the L2
 // slice cap; the output-stationary form needs 3x that).  Per row tile: 16 K-steps x two N=128 MMAs into two of three
 // 128-column TMEM accumulators; eight epilogue warps drain them (parity by the 2^23 trick), and XOR the 128 x 128-bit
 // result into C with red.global (partial sums over K chunks combine by XOR, so C starts zeroed).
@@ -169,7 +169,8 @@ void launch_tc_leaf_simple(DView C, DView A, DView Bt, bool accumulate, cudaStre
 namespace m4b {
 namespace {
 
-constexpr int kStageBytes = 16384, kBSubBytes = 32768, kSubs = 4, kAStages = 5;
+constexpr int kSubBytes = 16384;      // A sub-image: 128 rows x 256 elements
+constexpr int kStageBytes = 2 * kSubBytes, kBSubBytes = 32768, kSubs = 4, kAStages = 3;   // an A stage = two sub-images
 constexpr int kPanelBytes = kSubs * kBSubBytes;
 constexpr int kTc2Threads = 320;
 constexpr int kTc2Smem = kPanelBytes + kAStages * kStageBytes + 256 + 1024;   // + barriers + alignment slack
@@ -264,11 +265,14 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
       for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
         int const p = job / jobs_per_product, rem = job % jobs_per_product, kc = rem / args.npanels, np = rem % args.npanels;
         uint8_t const *srcB = args.imgB[p] + ((long long)(np * args.nkc + kc) * kSubs) * kBSubBytes;
-        for (int s = 0; s < kSubs; ++s) {       // each sub-image of the panel as soon as the previous job has let go of it
-          mbar_wait(empty_b(s), (ji & 1u) ^ 1u);
-          mbar_expect_tx(full_b(s), kBSubBytes);
-          bulk_g2s(sB + s * kBSubBytes, srcB + (long long)s * kBSubBytes, kBSubBytes, full_b(s));
-        }
+        auto load_panel_half = [&](int s0) {     // two sub-images of the panel as soon as the previous job has let go of them
+          for (int s = s0; s < s0 + 2; ++s) {
+            mbar_wait(empty_b(s), (ji & 1u) ^ 1u);
+            mbar_expect_tx(full_b(s), kBSubBytes);
+            bulk_g2s(sB + s * kBSubBytes, srcB + (long long)s * kBSubBytes, kBSubBytes, full_b(s));
+          }
+        };
+        load_panel_half(0);
         {                                        // ... and the next job's panel into L2 meanwhile
           int const nj = job + gridDim.x;
           if (nj < njobs) {
@@ -279,16 +283,17 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
           }
         }
         for (int mt = 0; mt < args.mtiles; ++mt) {
-          uint8_t const *srcA = args.imgA[p] + ((long long)(mt * args.nkc + kc) * kSubs) * kStageBytes;
-          if (mt + 2 < args.mtiles)       // the ring holds little more than one row tile: warm L2 two tiles ahead
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(srcA + 2ll * args.nkc * kSubs * kStageBytes),
-                         "r"((uint32_t)(kSubs * kStageBytes)) : "memory");
-          for (int s = 0; s < kSubs; ++s) {
+          uint8_t const *srcA = args.imgA[p] + ((long long)(mt * args.nkc + kc) * kSubs) * kSubBytes;
+          if (mt + 2 < args.mtiles)       // the ring holds one and a half row tiles: warm L2 two tiles ahead
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(srcA + 2ll * args.nkc * kSubs * kSubBytes),
+                         "r"((uint32_t)(kSubs * kSubBytes)) : "memory");
+          for (int h = 0; h < 2; ++h) {
             uint32_t const st = a_stage;
             mbar_wait(empty_a(st), a_phase ^ 1u);
             if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1u; }
             mbar_expect_tx(full_a(st), kStageBytes);
-            bulk_g2s(sA + st * kStageBytes, srcA + (long long)s * kStageBytes, kStageBytes, full_a(st));
+            bulk_g2s(sA + st * kStageBytes, srcA + (long long)h * kStageBytes, kStageBytes, full_a(st));
+            if (mt == 0 && h == 0) load_panel_half(2);      // (the first tile's first stage does not wait for the whole panel)
           }
         }
       }
@@ -305,72 +310,59 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
     uint32_t const sfa = tmem + 384u, sfb = tmem + 416u;
     uint32_t const desc_hi = (1024u >> 4) | (1u << 14), lbo = (128u >> 4) << 16;     // SBO, descriptor version | LBO
     uint32_t a_stage = 0, a_phase = 0, ji = 0, tile_ctr = 0;
-    auto commit_elect = [&](uint32_t bar) {
-      asm volatile("{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
-                   "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
-    };
-    // four K-steps of one sub-image, issued by one elected lane; the warp runs this convergently
-    auto mma4 = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool first_overwrites, uint32_t commit_bar) {
+    // eight K-steps (two sub-images = one A stage), issued by one elected lane, then up to three commits; the warp runs
+    // this convergently.  Descriptor low words: +16 per K-step (256 B), +1024 / +2048 for the second sub-image of A / B.
+#define TC_MMA_STEP(AOFF, BOFF, PRED)                                                                             \
+  "add.u32 al, %1, " #AOFF ";\nadd.u32 bl, %2, " #BOFF ";\nmov.b64 da, {al, %6};\nmov.b64 db, {bl, %6};\n"        \
+  "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], " PRED ";\n"
+#define TC_COMMIT(N) "setp.ne.and.b32 pc, %" #N ", 0, pe;\n@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%" #N "];\n"
+    auto mma8 = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool first_overwrites, uint32_t c0, uint32_t c1, uint32_t c2) {
       asm volatile(
-          "{\n.reg .pred pe, pt, pf;\n.reg .b64 da, db;\n.reg .b32 al, bl;\n"
+          "{\n.reg .pred pe, pt, pf, pc;\n.reg .b64 da, db;\n.reg .b32 al, bl;\n"
           "elect.sync _|pe, 0xffffffff;\n"
           "setp.eq.b32 pt, 0, 0;\nsetp.ne.b32 pf, %7, 0;\n"
-          "mov.b64 da, {%1, %6};\nmov.b64 db, {%2, %6};\n"
-          "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], pf;\n"
-          "add.u32 al, %1, 16;\nadd.u32 bl, %2, 16;\nmov.b64 da, {al, %6};\nmov.b64 db, {bl, %6};\n"
-          "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], pt;\n"
-          "add.u32 al, %1, 32;\nadd.u32 bl, %2, 32;\nmov.b64 da, {al, %6};\nmov.b64 db, {bl, %6};\n"
-          "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], pt;\n"
-          "add.u32 al, %1, 48;\nadd.u32 bl, %2, 48;\nmov.b64 da, {al, %6};\nmov.b64 db, {bl, %6};\n"
-          "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%4], [%5], pt;\n"
-          "setp.ne.and.b32 pe, %8, 0, pe;\n"
-          "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n}"
-          ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(sfa), "r"(sfb), "r"(desc_hi), "r"(first_overwrites ? 0u : 1u), "r"(commit_bar)
+          TC_MMA_STEP(0, 0, "pf") TC_MMA_STEP(16, 16, "pt") TC_MMA_STEP(32, 32, "pt") TC_MMA_STEP(48, 48, "pt")
+          TC_MMA_STEP(1024, 2048, "pt") TC_MMA_STEP(1040, 2064, "pt") TC_MMA_STEP(1056, 2080, "pt") TC_MMA_STEP(1072, 2096, "pt")
+          TC_COMMIT(8) TC_COMMIT(9) TC_COMMIT(10)
+          "}"
+          ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(sfa), "r"(sfb), "r"(desc_hi), "r"(first_overwrites ? 0u : 1u), "r"(c0), "r"(c1), "r"(c2)
           : "memory");
     };
+#undef TC_MMA_STEP
     for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++ji) {
       for (int mt = 0; mt < args.mtiles; ++mt, ++tile_ctr) {
         uint32_t const odd = tile_ctr & 1u, rfree = odd ? 2u : 0u;        // this tile: regions {rfree, 1}
         uint32_t const dbase = tmem + odd * 128u;                          // panel column c <-> TMEM column odd * 128 + c
         uint32_t const hfree = odd ? 1u : 0u, hmid = hfree ^ 1u;           // panel halves living in rfree / R1
-        auto next_stage = [&](uint32_t &st) {
-          st = a_stage;
-          mbar_wait(full_a(st), a_phase);
-          if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1u; }
-        };
-        auto a_desc = [&](uint32_t st) { return ((sA + st * kStageBytes) >> 4) | lbo; };
-        auto b_desc = [&](int s) { return ((sB + s * kBSubBytes) >> 4) | lbo; };
-        uint32_t st0, st1, st2;
-        // sub-images 0 and 1 as N = 128 halves: first the half whose region nobody else uses (512 cycles of work), then,
-        // once the previous tile's other half has been drained from R1, the R1 half; sub-images 2 and 3 as N = 256
         bool const first = mt == 0, last = mt + 1 == args.mtiles;    // of this job: the panel arrives / is let go piecewise
-        next_stage(st0);
-        if (first) mbar_wait(full_b(0), ji & 1u);
+        uint32_t const b01 = ((sB) >> 4) | lbo, b23 = ((sB + 2 * kBSubBytes) >> 4) | lbo;
+        // sub-images 0 and 1 (one stage) as N = 128 halves: first the half whose region nobody else uses (512 cycles of
+        // work), then, once the previous tile's other half has been drained from R1, the R1 half
+        uint32_t const st0 = a_stage;
+        mbar_wait(full_a(st0), a_phase);
+        if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1u; }
+        if (first) { mbar_wait(full_b(0), ji & 1u); mbar_wait(full_b(1), ji & 1u); }
         mbar_wait(acc_empty(rfree), ((tile_ctr >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        mma4(tmem + rfree * 128u, a_desc(st0), b_desc(0) + hfree * 1024u, idesc128, true, 0u);
-        next_stage(st1);
-        if (first) mbar_wait(full_b(1), ji & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        mma4(tmem + rfree * 128u, a_desc(st1), b_desc(1) + hfree * 1024u, idesc128, false, 0u);
+        uint32_t const a0 = ((sA + st0 * kStageBytes) >> 4) | lbo;
+        mma8(tmem + rfree * 128u, a0, b01 + hfree * 1024u, idesc128, true, 0u, 0u, 0u);
         mbar_wait(acc_empty(1), (tile_ctr & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        mma4(tmem + 128u, a_desc(st0), b_desc(0) + hmid * 1024u, idesc128, true, empty_a(st0));
-        if (last) commit_elect(empty_b(0));
-        mma4(tmem + 128u, a_desc(st1), b_desc(1) + hmid * 1024u, idesc128, false, empty_a(st1));
-        if (last) commit_elect(empty_b(1));
-#pragma unroll
-        for (int s = 2; s < kSubs; ++s) {
-          next_stage(st2);
-          if (first) mbar_wait(full_b(s), ji & 1u);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          mma4(dbase, a_desc(st2), b_desc(s), idesc256, false, empty_a(st2));
-          if (last) commit_elect(empty_b(s));
-        }
-        commit_elect(acc_full(1));
-        commit_elect(acc_full(rfree));
+        mma8(tmem + 128u, a0, b01 + hmid * 1024u, idesc128, true, empty_a(st0), last ? empty_b(0) : 0u, last ? empty_b(1) : 0u);
+        // sub-images 2 and 3 as N = 256
+        uint32_t const st1 = a_stage;
+        mbar_wait(full_a(st1), a_phase);
+        if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1u; }
+        if (first) { mbar_wait(full_b(2), ji & 1u); mbar_wait(full_b(3), ji & 1u); }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mma8(dbase, ((sA + st1 * kStageBytes) >> 4) | lbo, b23, idesc256, false, empty_a(st1), last ? empty_b(2) : 0u, last ? empty_b(3) : 0u);
+        asm volatile("{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+                     "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                     "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n}"
+                     ::"r"(acc_full(1)), "r"(acc_full(rfree)) : "memory");
       }
     }
+#undef TC_COMMIT
   } else {                       // ---------------- epilogue: warps 2..9 ----------------
     // every warp drains 64 columns of R1 first — the region the next tile is waiting for —, then 64 columns of R0 / R2
     int const q = warp & 3, hsel = (warp - 2) >> 2;
