@@ -480,12 +480,14 @@ static bool tall_leaf(int m, int l, int n, bool overwrite) {
   return !overwrite && (variant == 2 || ((variant == 0 || variant == 3) && leaf2_suits(m, l, n)));
 }
 
-// the tensor-core leaf: C = A*B only (it overwrites C), shapes in its tile units, 16-byte aligned rows of B
+// the tensor-core leaf: C = A*B only (it overwrites C), shapes in its tile units, 16-byte aligned rows
 static bool tensor_leaf(int count, DView const *C, DView const *A, DView const *B, bool clear_first) {
   int const variant = leaf_variant();
   if ((variant != 0 && variant != 3) || !clear_first || count > 49 || !tc_leaf_suits(A[0].nrows, A[0].ncols, B[0].ncols)) return false;
   for (int i = 0; i < count; ++i)
-    if ((reinterpret_cast<uintptr_t>(B[i].data) & 15) || (B[i].pitch & 1)) return false;
+    if (((reinterpret_cast<uintptr_t>(A[i].data) | reinterpret_cast<uintptr_t>(B[i].data) | reinterpret_cast<uintptr_t>(C[i].data)) & 15) ||
+        ((A[i].pitch | B[i].pitch | C[i].pitch) & 1))
+      return false;
   return true;
 }
 

@@ -427,23 +427,35 @@ struct TcPrepArgs {
   int m, l, n, nkc;
 };
 
-// A operands: bits of A (m x l) -> the tiled e2m1 image, one thread per 16-byte core-matrix row (32 elements);
-// blockIdx.y = product.  The same threads clear C (the main kernel XORs partial sums into it).
+// A operands: bits of A (m x l) -> the tiled e2m1 image.  One thread per (row, 256-element sub-image): it reads the 32
+// bytes of its row (one sector) and writes the eight 16-byte core-matrix rows they expand to, 128 bytes apart — the eight
+// rows of a group (consecutive lanes) fill whole 128-byte lines.  blockIdx.y = product.
 __global__ void __launch_bounds__(256) tc_expand_a_kernel(const __grid_constant__ TcPrepArgs a) {
   int const p = blockIdx.y;
-  long long const total = (long long)a.m * a.l / 32;
-  long long const o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o < total) {
-    long long const sub = o / (128 * 8);
-    int const within = (int)(o % (128 * 8)), rg = within / 64, kg = (within / 8) % 8, r8 = within % 8;
-    int const s = (int)(sub % kSubs), kc = (int)((sub / kSubs) % a.nkc);
-    long long const tile = sub / ((long long)kSubs * a.nkc);
-    long long const row = tile * 128 + rg * 8 + r8;
-    uint32_t const bits = reinterpret_cast<uint32_t const *>(a.A[p] + row * a.pitchA[p])[kc * 32 + s * 8 + kg];
-    reinterpret_cast<uint4 *>(a.imgA[p])[o] = make_uint4(expand8(bits), expand8(bits >> 8), expand8(bits >> 16), expand8(bits >> 24));
-  }
-  long long const cwords = (long long)a.m * (a.n / 64);            // C: m rows of n / 64 words
-  for (long long w = o; w < cwords; w += (long long)gridDim.x * blockDim.x) a.C[p][(w / (a.n / 64)) * a.pitchC[p] + w % (a.n / 64)] = 0;
+  long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (tile, kc, s, row group, row in group)
+  if (t >= (long long)a.m * a.l / 256) return;
+  int const r8 = (int)(t & 7), rg = (int)((t >> 3) & 15);
+  long long const sub = t >> 7;                                               // 128 rows per sub-image
+  int const s = (int)(sub % kSubs), kc = (int)((sub / kSubs) % a.nkc);
+  long long const tile = sub / ((long long)kSubs * a.nkc);
+  long long const row = tile * 128 + rg * 8 + r8;
+  uint4 const *src = reinterpret_cast<uint4 const *>(a.A[p] + row * a.pitchA[p] + kc * 16 + s * 4);
+  uint4 const lo = src[0], hi = src[1];
+  uint32_t const x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint4 *dst = reinterpret_cast<uint4 *>(a.imgA[p] + sub * kSubBytes + rg * 1024 + r8 * 16);
+#pragma unroll
+  for (int kg = 0; kg < 8; ++kg)
+    dst[kg * 8] = make_uint4(expand8(x[kg]), expand8(x[kg] >> 8), expand8(x[kg] >> 16), expand8(x[kg] >> 24));
+}
+
+// C = 0 for every product (the main kernel XORs partial sums into it); 16 bytes per thread, blockIdx.y = product
+__global__ void __launch_bounds__(256) tc_zero_c_kernel(const __grid_constant__ TcPrepArgs a) {
+  int const p = blockIdx.y, w16 = a.n / 128;
+  long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)a.m * w16) return;
+  long long const row = t / w16;
+  int const c = (int)(t % w16);
+  reinterpret_cast<uint4 *>(a.C[p] + row * a.pitchC[p])[c] = make_uint4(0, 0, 0, 0);
 }
 
 // lane i holds row i of a 32 x 32 bit block (column j in bit j); returns column `lane` as a row
@@ -526,7 +538,8 @@ void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, 
   if (reuse && count == 1 && last_a == A[0].data && last_b == B[0].data) {
     M4B_CUDA(cudaMemset2DAsync(C[0].data, C[0].pitch * sizeof(word), 0, (size_t)(n / 64) * sizeof(word), m, s));
   } else {
-    tc_expand_a_kernel<<<dim3((unsigned)((units + 255) / 256), count), 256, 0, s>>>(prep);
+    tc_expand_a_kernel<<<dim3((unsigned)((units / 8 + 255) / 256), count), 256, 0, s>>>(prep);
+    tc_zero_c_kernel<<<dim3((unsigned)(((long long)m * (n / 128) + 255) / 256), count), 256, 0, s>>>(prep);
     tc_expand_bt_kernel<<<dim3(n / 256, l / 256, count), 256, 0, s>>>(prep);
     last_a = A[0].data; last_b = B[0].data;
   }
@@ -538,7 +551,7 @@ void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, 
   int const njobs = count * args.nkc * args.npanels, grid = njobs < m4rm_num_sms() ? njobs : m4rm_num_sms();
   tc_leaf2_kernel<<<grid, kTc2Threads, kTc2Smem, s>>>(args);
   M4B_CUDA(cudaGetLastError());
-  g_kernel_launches += 3;
+  g_kernel_launches += 4;
 }
 
 void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) { launch_tc_batch(1, &C, &A, &B, s); }
