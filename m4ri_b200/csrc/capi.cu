@@ -270,6 +270,19 @@ struct HostOverlap : TopHooks {
   }
 };
 
+// Padded operand dimensions: every Strassen level must halve exactly (rows: 2^levels, columns: 128 * 2^levels).  When
+// the leaves are big enough for the tensor-core leaf (tc_leaf.cu) and it may be used, the units are ITS tile units
+// (128 rows, 1024 inner bits, 256 columns per leaf) — at most a quarter more work in the worst case for a leaf that is
+// 1.7x faster, and nothing at all for the power-of-two sizes.  Zero padding never changes a result bit.
+void padded_dims(int m, int l, int n, int levels, int *mp, int *lp, int *np) {
+  int um = 1, ul = 128, un = 128;
+  bool const tensor_ok = g_leaf_variant != 1 && g_leaf_variant != 2;
+  if (tensor_ok && (m >> levels) >= 512 && (l >> levels) >= 4096 && (n >> levels) >= 1024) { um = 128; ul = 1024; un = 256; }
+  *mp = round_up(m, um << levels);
+  *lp = round_up(l > 0 ? l : 1, ul << levels);
+  *np = round_up(n, un << levels);
+}
+
 // The one host->device->host product path behind every reference-named entry point.
 void host_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool clear, bool strassen) {
   M4B_LOCKED;
@@ -278,7 +291,8 @@ void host_product(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff, bool cle
   if (m == 0 || n == 0) return;
   ++g_products;
   int const levels = (strassen && l > 0) ? strassen_levels(m, l, n, cutoff) : 0;
-  int const mp = round_up(m, 1 << levels), lp = round_up(l > 0 ? l : 1, 128 << levels), np = round_up(n, 128 << levels);
+  int mp, lp, np;
+  padded_dims(m, l, n, levels, &mp, &lp, &np);
   snprintf(c.last_path, sizeof c.last_path, levels ? "strassen:%d" : "m4rm", levels);
 
   size_t const need = Workspace::bytes_for(mp, lp) + Workspace::bytes_for(lp, np) + Workspace::bytes_for(mp, np) +
@@ -363,7 +377,8 @@ void device_product(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat c
     return;
   }
   snprintf(c.last_path, sizeof c.last_path, levels ? "strassen:%d" : "m4rm", levels);
-  int const mp = round_up(m, 1 << levels), lp = round_up(l, 128 << levels), np = round_up(n, 128 << levels);
+  int mp, lp, np;
+  padded_dims(m, l, n, levels, &mp, &lp, &np);
   bool const pad = levels > 0 && (mp != m || lp != l || np != n);
   if (!pad) {
     c.ws.reserve(strassen_workspace_bytes(m, l, n, levels));

@@ -491,13 +491,28 @@ static bool tensor_leaf(int count, DView const *C, DView const *A, DView const *
   return true;
 }
 
-int m4rm_batch_limit(int m, int l, int n) { return tall_leaf(m, l, n, false) ? 49 : kMaxBatch; }
+static int m4rm_only_batch_limit(int m, int l, int n) { return tall_leaf(m, l, n, false) ? 49 : kMaxBatch; }
+
+// products per launch the scheduler may ask for: 49 where the tensor-core or the tall-tile leaf takes the shape
+int m4rm_batch_limit(int m, int l, int n) {
+  int const variant = leaf_variant();
+  if ((variant == 0 || variant == 3) && tc_leaf_suits(m, l, n)) return 49;
+  return m4rm_only_batch_limit(m, l, n);
+}
 
 static void launch_leaf(int count, DView const *C, DView const *A, DView const *B, bool overwrite, cudaStream_t stream,
                         bool clear_first = false) {
   if (count <= 0 || A[0].nrows <= 0 || A[0].ncols <= 0 || B[0].ncols <= 0) return;   // empty product: C unchanged
-  if (count > m4rm_batch_limit(A[0].nrows, A[0].ncols, B[0].ncols))
-    die("m4ri_b200: batch of %d leaf products exceeds the limit of this leaf\n", count);
+  bool const tensor = !overwrite && tensor_leaf(count, C, A, B, clear_first);
+  if (!tensor) {
+    // a batch sized for the tensor-core leaf that cannot take it after all (accumulating form, unaligned views): in pieces
+    int const limit = m4rm_only_batch_limit(A[0].nrows, A[0].ncols, B[0].ncols);
+    if (count > limit) {
+      for (int i = 0; i < count; i += limit)
+        launch_leaf(count - i < limit ? count - i : limit, C + i, A + i, B + i, overwrite, stream, clear_first);
+      return;
+    }
+  }
   std::pair<cudaEvent_t, cudaEvent_t> *ev = nullptr;
   int cur_dev = -1;
   if (g_prof.on) cudaGetDevice(&cur_dev);
@@ -512,7 +527,7 @@ static void launch_leaf(int count, DView const *C, DView const *A, DView const *
     g_prof.bitops += 2.0 * count * A[0].nrows * (double)A[0].ncols * B[0].ncols;
     M4B_CUDA(cudaEventRecord(ev->first, stream));
   }
-  if (!overwrite && tensor_leaf(count, C, A, B, clear_first)) {
+  if (tensor) {
     g_last_leaf = 3;
     launch_tc_batch(count, C, A, B, stream);
     if (ev) M4B_CUDA(cudaEventRecord(ev->second, stream));
