@@ -36,6 +36,12 @@ for (m, n) in [(65, 63), (700, 1300)]:
     T = lib.m4ri_b200_transpose(None, A)
     ok &= H.equal(T, O.orc_transpose(None, A))
     print("transpose", m, n, "OK" if ok else "BAD", flush=True)
+# round 2: the tensor-core leaf (bulk copies, mbarriers, TMEM, red.xor epilogue) alone and under one Strassen level
+for (m, l, n, cutoff) in [(256, 1024, 256, 0), (384, 2048, 512, 0), (1024, 4096, 1024, 512)]:
+    A, B = H.random_matrix(m, l), H.random_matrix(l, n)
+    P = lib.mzd_mul(None, A, B, cutoff) if cutoff else lib.mzd_mul_m4rm(None, A, B, 0)
+    ok &= H.equal(P, O.orc_mul(None, A, B, 0)) and lib.m4ri_b200_last_leaf_variant() == 3
+    print("tensor leaf", m, l, n, cutoff, lib.m4ri_b200_last_path().decode(), "OK" if ok else "BAD", flush=True)
 # round 2: the tall-tile leaf with the hybrid partition and store mode under a two-level Strassen node with the fused
 # two-level additions (8192^3 at cutoff 2048 with the tall leaf forced: 49 products of 2048^3 in one launch), and the
 # accumulating form; checked by Freivalds (the scalar oracle is too slow under the sanitizer at this size)
