@@ -130,7 +130,7 @@ void launch_tc_leaf_simple(DView C, DView A, DView Bt, bool accumulate, cudaStre
 void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s);        // pipelined B-stationary form, C = A * B
 bool tc_leaf_suits(int m, int l, int n);
 void tc_scratch_release();
-void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t s);   // <= 49 products, C overwritten
+void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t s, bool accumulate);   // <= 49 products
 
 // ---- PLE decomposition (ple.cu) ----------------------------------------------------------------
 // in place on a device-resident matrix; P (nrows ints) and Q (ncols ints) on the host; returns the rank, synchronises s

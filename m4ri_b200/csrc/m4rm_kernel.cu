@@ -480,10 +480,10 @@ static bool tall_leaf(int m, int l, int n, bool overwrite) {
   return !overwrite && (variant == 2 || ((variant == 0 || variant == 3) && leaf2_suits(m, l, n)));
 }
 
-// the tensor-core leaf: C = A*B only (it overwrites C), shapes in its tile units, 16-byte aligned rows
-static bool tensor_leaf(int count, DView const *C, DView const *A, DView const *B, bool clear_first) {
+// the tensor-core leaf: C = A*B and C ^= A*B (not the in-place overwrite form), shapes in its tile units, 16-byte aligned rows
+static bool tensor_leaf(int count, DView const *C, DView const *A, DView const *B) {
   int const variant = leaf_variant();
-  if ((variant != 0 && variant != 3) || !clear_first || count > 49 || !tc_leaf_suits(A[0].nrows, A[0].ncols, B[0].ncols)) return false;
+  if ((variant != 0 && variant != 3) || count > 49 || !tc_leaf_suits(A[0].nrows, A[0].ncols, B[0].ncols)) return false;
   for (int i = 0; i < count; ++i)
     if (((reinterpret_cast<uintptr_t>(A[i].data) | reinterpret_cast<uintptr_t>(B[i].data) | reinterpret_cast<uintptr_t>(C[i].data)) & 15) ||
         ((A[i].pitch | B[i].pitch | C[i].pitch) & 1))
@@ -503,9 +503,9 @@ int m4rm_batch_limit(int m, int l, int n) {
 static void launch_leaf(int count, DView const *C, DView const *A, DView const *B, bool overwrite, cudaStream_t stream,
                         bool clear_first = false) {
   if (count <= 0 || A[0].nrows <= 0 || A[0].ncols <= 0 || B[0].ncols <= 0) return;   // empty product: C unchanged
-  bool const tensor = !overwrite && tensor_leaf(count, C, A, B, clear_first);
+  bool const tensor = !overwrite && tensor_leaf(count, C, A, B);
   if (!tensor) {
-    // a batch sized for the tensor-core leaf that cannot take it after all (accumulating form, unaligned views): in pieces
+    // a batch sized for the tensor-core leaf that cannot take it after all (unaligned views): in pieces
     int const limit = m4rm_only_batch_limit(A[0].nrows, A[0].ncols, B[0].ncols);
     if (count > limit) {
       for (int i = 0; i < count; i += limit)
@@ -529,7 +529,7 @@ static void launch_leaf(int count, DView const *C, DView const *A, DView const *
   }
   if (tensor) {
     g_last_leaf = 3;
-    launch_tc_batch(count, C, A, B, stream);
+    launch_tc_batch(count, C, A, B, stream, !clear_first);
     if (ev) M4B_CUDA(cudaEventRecord(ev->second, stream));
     return;
   }

@@ -499,8 +499,9 @@ std::mutex g_tc_mu;
 
 bool tc_leaf_suits(int m, int l, int n) { return m >= 128 && m % 128 == 0 && l >= 1024 && l % 1024 == 0 && n >= 256 && n % 256 == 0; }
 
-// C[i] = A[i] * B[i] for up to 49 products of one shape on the tensor cores (C is overwritten)
-void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t s) {
+// C[i] = A[i] * B[i] (C overwritten) or, with `accumulate`, C[i] ^= A[i] * B[i] — the kernel XORs its partial results into C
+// either way, so the accumulating form just leaves out the clearing of C — for up to 49 products of one shape
+void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, cudaStream_t s, bool accumulate) {
   int const m = A[0].nrows, l = A[0].ncols, n = B[0].ncols;
   if (count < 1 || count > kTcMaxBatch || !tc_leaf_suits(m, l, n))
     die("m4ri_b200: tensor-core leaf needs <= 49 products with m %% 128 == 0, l %% 1024 == 0, n %% 256 == 0\n");
@@ -536,10 +537,10 @@ void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, 
   static word const *last_a = nullptr, *last_b = nullptr;
   long long const units = (long long)m * l / 32;
   if (reuse && count == 1 && last_a == A[0].data && last_b == B[0].data) {
-    M4B_CUDA(cudaMemset2DAsync(C[0].data, C[0].pitch * sizeof(word), 0, (size_t)(n / 64) * sizeof(word), m, s));
+    if (!accumulate) M4B_CUDA(cudaMemset2DAsync(C[0].data, C[0].pitch * sizeof(word), 0, (size_t)(n / 64) * sizeof(word), m, s));
   } else {
     tc_expand_a_kernel<<<dim3((unsigned)((units / 8 + 255) / 256), count), 256, 0, s>>>(prep);
-    tc_zero_c_kernel<<<dim3((unsigned)(((long long)m * (n / 128) + 255) / 256), count), 256, 0, s>>>(prep);
+    if (!accumulate) tc_zero_c_kernel<<<dim3((unsigned)(((long long)m * (n / 128) + 255) / 256), count), 256, 0, s>>>(prep);
     tc_expand_bt_kernel<<<dim3(n / 256, l / 256, count), 256, 0, s>>>(prep);
     last_a = A[0].data; last_b = B[0].data;
   }
@@ -554,7 +555,7 @@ void launch_tc_batch(int count, DView const *C, DView const *A, DView const *B, 
   g_kernel_launches += 4;
 }
 
-void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) { launch_tc_batch(1, &C, &A, &B, s); }
+void launch_tc_leaf2(DView C, DView A, DView B, cudaStream_t s) { launch_tc_batch(1, &C, &A, &B, s, false); }
 
 // frees the operand-image scratch of every device (m4ri_b200_release)
 void tc_scratch_release() {

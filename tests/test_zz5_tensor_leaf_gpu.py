@@ -1,5 +1,5 @@
 """GPU parity of the tensor-core leaf (tc_leaf.cu: tcgen05.mma kind::mxf4 on bits expanded to e2m1, fp32 accumulators in
-TMEM, parity epilogue) — the automatic leaf for C = A*B products whose dimensions are in its tile units (m % 128,
+TMEM, parity epilogue) — the automatic leaf for C = A*B and C ^= A*B products whose dimensions are in its tile units (m % 128,
 l % 1024, n % 256), i.e. the Strassen leaves of every large product.
 
 It is compared bit for bit with the oracle (small shapes), with the M4RM leaves on the same device-resident operands
@@ -168,13 +168,15 @@ def test_strassen_batches_of_tensor_leaves(lib, n, cutoff, launches):
     H.free(A, B, *res)
 
 
-def test_accumulating_products_keep_the_m4rm_leaf(lib):
-    """C ^= A*B at leaf level (mzd_addmul_m4rm) is not a tensor-leaf case (it overwrites C): the M4RM leaf must serve it."""
-    H.libc.srandom(5)
-    A, B, C = H.random_matrix(256, 1024, ), H.random_matrix(1024, 256), H.random_matrix(256, 256)
+@pytest.mark.parametrize("m,l,n", [(256, 1024, 256), (640, 3072, 768)])
+def test_accumulating_products_on_the_tensor_leaf(lib, m, l, n):
+    """C ^= A*B at leaf level (mzd_addmul_m4rm): the kernel XORs its partial results into C, so the accumulating form is
+    the same kernel without the clearing of C."""
+    H.libc.srandom(5 + m)
+    A, B, C = H.random_matrix(m, l), H.random_matrix(l, n), H.random_matrix(m, n)
     want = H.oracle().orc_mul_m4rm(H.clone(C), A, B, 0, 0)
     lib.mzd_addmul_m4rm(C, A, B, 0)
-    assert lib.m4ri_b200_last_leaf_variant() in (1, 2)
+    assert lib.m4ri_b200_last_leaf_variant() == 3
     assert H.equal(C, want)
     H.free(A, B, C, want)
 

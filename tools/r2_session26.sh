@@ -1,5 +1,6 @@
 #!/bin/bash
-# round 2, session 26: pipelined leaf nodes (LeafPipe) — digests, timing with and without the pipe
+# round 2, session 26: pipelined leaf nodes (LeafPipe, M4RI_B200_NO_PIPE) — an experiment that was REMOVED again:
+# this script documents how it was measured and no longer toggles anything
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_large_golden_gpu.py tests/test_zz5_tensor_leaf_gpu.py -x -q 2>&1 | tail -2
 for np in 1 0; do
