@@ -168,6 +168,33 @@ def test_strassen_batches_of_tensor_leaves(lib, n, cutoff, launches):
     H.free(A, B, *res)
 
 
+@pytest.mark.parametrize("m,l,n,cutoff,path", [(5000, 9000, 3000, 0, "m4rm"), (9000, 18000, 6000, 4096, "strassen:1"),
+                                               (5003, 8999, 3001, 0, "m4rm")])
+def test_odd_shapes_are_padded_to_the_tile_units(lib, m, l, n, cutoff, path):
+    """Sizes that are no multiples of anything: the host path pads the device operands with zeros to the tensor leaf's tile
+    units (capi.cu: padded_dims), the result window is what the M4RM-only schedule gives, bit for bit, and passes
+    Freivalds' check."""
+    rng = np.random.default_rng(m + n)
+    A, B = H.new(m, l), H.new(l, n)
+    for M in (A, B):
+        st = H.storage(M)
+        st[:, :] = rng.integers(0, 2**64, size=st.shape, dtype=np.uint64)
+        st[:, M.contents.width - 1] &= np.uint64(M.contents.high_bitmask)
+        st[:, M.contents.width:] = 0
+    res = []
+    for variant in (2, 0):
+        lib.m4ri_b200_set_leaf_variant(variant)
+        C = H.new(m, n)
+        lib.mzd_mul(C, A, B, cutoff)
+        if variant == 0:
+            assert lib.m4ri_b200_last_path().decode() == path
+            assert lib.m4ri_b200_last_leaf_variant() == 3
+        res.append(C)
+    lib.m4ri_b200_set_leaf_variant(0)
+    assert np.array_equal(H.storage(res[0]), H.storage(res[1]))
+    H.free(A, B, *res)
+
+
 @pytest.mark.parametrize("m,l,n", [(256, 1024, 256), (640, 3072, 768)])
 def test_accumulating_products_on_the_tensor_leaf(lib, m, l, n):
     """C ^= A*B at leaf level (mzd_addmul_m4rm): the kernel XORs its partial results into C, so the accumulating form is
