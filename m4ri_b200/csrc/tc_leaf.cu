@@ -181,7 +181,7 @@ struct Tc2Args {
   uint8_t const *imgA[kTcMaxBatch];
   uint8_t const *imgB[kTcMaxBatch];
   int pitchC[kTcMaxBatch];
-  int count, mtiles, nkc, npanels, flags;   // flags: experiment bits (1 skip the parity math)
+  int count, mtiles, nkc, npanels, flags;   // flags: experiment bits (1 skip the parity arithmetic, 2 skip the TMEM drain: timing only)
 };
 
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
@@ -370,6 +370,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc_leaf2_kernel(const __grid_c
     auto drain = [&](uint32_t region, uint32_t parity, word *dst) {
       mbar_wait(acc_full(region), parity);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (args.flags & 2) {                              // timing experiment: hand the region back without reading it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(region));
+        return;
+      }
       uint32_t v[64];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
