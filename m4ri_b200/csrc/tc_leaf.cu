@@ -1,12 +1,15 @@
-// tc_leaf.cu — EXPERIMENTAL tensor-core leaf (not on any default path; m4ri_b200_dmul_tc only).
+// tc_leaf.cu — the tensor-core leaf: C (^)= A * B over GF(2) on the 5th-generation tensor cores (sm_100a).
 //
-// C (^)= A * B over GF(2) on the 5th-generation tensor cores: the bits of A (rows) and of B^T (rows = columns of B) are
-// expanded to e2m1 nibbles (0 -> 0x0, 1 -> 0x2 = 1.0) in shared memory, multiplied with
-// tcgen05.mma.kind::mxf4.block_scale (unit ue8m0 scales, fp32 accumulators in TMEM, exact for 0/1 operands: integer
-// sums < 2^24 — profiles/r02_tensor_core_question.md), and the parity of every accumulator is packed back into the
-// bit-packed C.  This first form is output-stationary and single-buffered — it exists to validate the data path
-// (nibble layout, descriptors, mbarrier phases, parity epilogue) bit for bit against the M4RM leaf, not to be fast.
-// Shapes: m % 128 == 0, n % 256 == 0, l % 128 == 0; Bt is B transposed (n x l).
+// The bits of A (rows) and of B (columns) are expanded to e2m1 nibbles (0 -> 0x0, 1 -> 0x2 = 1.0), multiplied with
+// tcgen05.mma.kind::mxf4.block_scale (unit ue8m0 scales, fp32 accumulators in TMEM; exact for 0/1 operands: every partial
+// sum is an integer < 2^24 — profiles/r02_tensor_core_question.md), and the parity of every accumulator is packed back
+// into the bit-packed C.  Replaces, for the shapes it suits, the M4RM leaf of brilliantrussian.c:999-1190 with the same
+// result bits (tests/test_zz5_tensor_leaf_gpu.py, the reference digests of tests/golden/large_golden.json).
+//
+// Two forms live here.  FIRST a small output-stationary, single-buffered kernel (m4ri_b200_dmul_tc only) that expands in
+// shared memory — it validated the data path (nibble layout, descriptors, mbarrier phases, parity epilogue) and is kept as
+// an independent cross-check; shapes m % 128 == 0, n % 256 == 0, l % 128 == 0, Bt = B transposed (n x l).  Then the
+// production kernel (second half of the file).
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -155,16 +158,17 @@ void launch_tc_leaf_simple(DView C, DView A, DView Bt, bool accumulate, cudaStre
 }  // namespace m4b
 
 // =====================================================================================================================
-// Second form: B-stationary, pipelined, warp-specialised.  The operands are expanded to e2m1 ONCE by a streaming
-// pre-pass into "images" whose pieces are exactly the shared-memory operand layout, so the main kernel moves them with
-// plain bulk copies (cp.async.bulk + mbarrier complete_tx):
+// The production form: B-stationary, pipelined, warp-specialised.  The operands are expanded to
+// e2m1 ONCE by a streaming pre-pass into "images" whose pieces are exactly the shared-memory operand layout, so the main
+// kernel moves them with plain bulk copies (cp.async.bulk + mbarrier complete_tx):
 //   A image:  [row tile of 128][K chunk of 1024][sub 0..3] x 16 KB   (sub-image = 128 rows x 256 elements)
-//   B image:  [column panel of 256][K chunk][sub 0..3]     x 32 KB   (rows = columns of B, from B^T)
+//   B image:  [column panel of 256][K chunk][sub 0..3]     x 32 KB   (rows = columns of B: the expansion transposes)
 // A job = (product, K chunk, column panel): the 128 KB panel chunk stays in shared memory while EVERY row tile of A
-// streams past it through a ring of three 32 KB stages (two sub-images each) (4 KB of L2 traffic per 128-cycle MMA pair = 31 B/clk/SM, under the L2
-// slice cap; the output-stationary form needs 3x that).  Per row tile: 16 K-steps x two N=128 MMAs into two of three
-// 128-column TMEM accumulators; eight epilogue warps drain them (parity by the 2^23 trick), and XOR the 128 x 128-bit
-// result into C with red.global (partial sums over K chunks combine by XOR, so C starts zeroed).
+// streams past it through a ring of three 32 KB stages (two sub-images each): 4 KB of L2 traffic per 128-cycle MMA pair =
+// 31 B/clk/SM, well under the L2 slice limit (an output-stationary tile needs 3x that).  Per row tile: 16 K-steps into two
+// of three 128-column TMEM regions (N = 128 halves for the first stage, N = 256 for the second, see the MMA warp); eight
+// epilogue warps drain them (parity by the 2^23 trick) and XOR the result bits into C with red.global — partial sums
+// over K chunks combine by XOR, so C = A*B starts from a cleared C and C ^= A*B from C itself.
 // =====================================================================================================================
 namespace m4b {
 namespace {
