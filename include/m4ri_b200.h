@@ -196,12 +196,13 @@ typedef struct m4ri_b200_hooks {
 void m4ri_b200_dmul_quads(m4ri_b200_dmat *const C[4], m4ri_b200_dmat const *const A[4], m4ri_b200_dmat const *const B[4],
                           int cutoff, int clear, void *stream, m4ri_b200_hooks const *hooks);
 /* as dmul with the Strassen depth given explicitly (0 = leaf only); for cutoff sweeps. */
-/* EXPERIMENTAL, measurement only (profiles/r02_tensor_core_question.md): C = A*B (clear) or C ^= A*B with
- * tcgen05.mma kind::mxf4 on operands expanded to e2m1 in shared memory; Bt is B transposed (n x l);
- * m % 128 == 0, n % 256 == 0, l % 128 == 0.  Not used by any reference-named entry point. */
+/* Direct entry points of the tensor-core leaf (csrc/tc_leaf.cu) for tests and measurements; the reference-named entry
+ * points reach the same kernel through the automatic leaf choice (M4RI_B200_LEAF, m4ri_b200_set_leaf_variant).
+ * m4ri_b200_dmul_tc: the small output-stationary cross-check kernel, C = A*B (clear != 0) or C ^= A*B; Bt is B
+ * transposed (n x l); m % 128 == 0, n % 256 == 0, l % 128 == 0. */
 void m4ri_b200_dmul_tc(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *Bt, int clear, void *stream);
-/* EXPERIMENTAL: C = A*B with the pipelined B-stationary tensor-core kernel (operands expanded to e2m1 images by a
- * pre-pass); m % 128 == 0, l % 1024 == 0, n % 256 == 0. */
+/* m4ri_b200_dmul_tc2: C = A*B with the production kernel (operand images by a pre-pass, B-stationary pipeline);
+ * m % 128 == 0, l % 1024 == 0, n % 256 == 0, 16-byte aligned rows. */
 void m4ri_b200_dmul_tc2(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *B, void *stream);
 /* PLE of a device-resident matrix in place; P (nrows ints) and Q (ncols ints) are host arrays; returns the rank */
 rci_t m4ri_b200_dple(m4ri_b200_dmat *A, rci_t *P, rci_t *Q, void *stream);

@@ -908,7 +908,7 @@ rci_t m4ri_b200_dple(m4ri_b200_dmat *A, rci_t *P, rci_t *Q, void *stream) {
   return ple_device(as_view(A), P, Q, co, c.ws, stream ? static_cast<cudaStream_t>(stream) : c.stream);
 }
 
-// EXPERIMENTAL (measurement only): C (^)= A * B on the tensor cores; Bt = B transposed (m4ri_b200_dtranspose)
+// direct entry points of the tensor-core leaf (tests, measurements): the cross-check kernel (Bt = B transposed) ...
 void m4ri_b200_dmul_tc(m4ri_b200_dmat *C, m4ri_b200_dmat const *A, m4ri_b200_dmat const *Bt, int clear, void *stream) {
   M4B_LOCKED;
   ctx();
