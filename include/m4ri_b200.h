@@ -49,7 +49,7 @@ typedef struct mzd_t {
 } mzd_t;
 #endif
 
-/* C = A*B, Strassen-Winograd above the M4RM leaf.  C may be NULL (allocated, caller
+/* C = A*B, Strassen-Winograd above the leaf kernels (tensor-core / M4RM).  C may be NULL (allocated, caller
  * frees with mzd_free).  cutoff 0 = library default, <0 dies.  m4ri/strassen.h:52,
  * strassen.c:345-365. */
 mzd_t *mzd_mul(mzd_t *C, mzd_t const *A, mzd_t const *B, int cutoff);
@@ -123,8 +123,9 @@ int         m4ri_b200_get_default_cutoff(void);
 void        m4ri_b200_release(void);                    /* free cached device workspaces */
 char const *m4ri_b200_last_path(void);                  /* "m4rm" / "strassen:<levels>" of the last product */
 uint64_t    m4ri_b200_kernel_launches(void);            /* CUDA kernels launched by this library so far */
-/* M4RM leaf kernel: 0 = automatic, 1 = 1024 x 1024-bit tiles, 2 = 4096 x 256-bit tiles for every shape;
- * anything else = back to $M4RI_B200_LEAF / the built-in default.  Returns the previous setting. */
+/* Leaf kernel: 0 = automatic (the tensor-core leaf for products in its tile units, else the M4RM leaves), 1 = M4RM
+ * 1024 x 1024-bit tiles only, 2 = M4RM 4096 x 256-bit tiles for every shape, 3 = same as 0; anything else = back to
+ * $M4RI_B200_LEAF / the built-in default.  No choice changes a result bit.  Returns the previous setting. */
 int         m4ri_b200_set_leaf_variant(int variant);
 int         m4ri_b200_last_leaf_variant(void);          /* kernel of the last leaf launch: 1 or 2 (0: none yet) */
 
