@@ -127,7 +127,7 @@ uint64_t    m4ri_b200_kernel_launches(void);            /* CUDA kernels launched
  * 1024 x 1024-bit tiles only, 2 = M4RM 4096 x 256-bit tiles for every shape, 3 = same as 0; anything else = back to
  * $M4RI_B200_LEAF / the built-in default.  No choice changes a result bit.  Returns the previous setting. */
 int         m4ri_b200_set_leaf_variant(int variant);
-int         m4ri_b200_last_leaf_variant(void);          /* kernel of the last leaf launch: 1 or 2 (0: none yet) */
+int         m4ri_b200_last_leaf_variant(void);          /* kernel of the last leaf launch: 1, 2 (M4RM) or 3 (tensor-core); 0: none yet */
 
 /* Live timing of the M4RM leaf launches: between begin and end every leaf launch is bracketed
  * by CUDA events on its stream.  end() (call after synchronising) returns the number of leaf
