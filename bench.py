@@ -62,6 +62,27 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def bind_near_gpu(local):
+    """Restricts this rank to the CPUs NVML reports as local to its GPU (same NUMA node / PCIe root), BEFORE any pinned
+    host memory is allocated: with one rank per GPU all moving data at once, buffers that sit on the other socket cross
+    the inter-socket link and share its bandwidth.  Returns (previous affinity, description) or (None, why not)."""
+    try:
+        import pynvml
+        import torch
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & prev
+        if not cpus or cpus == prev:
+            return None, "NVML reports no narrower CPU set for this GPU"
+        os.sched_setaffinity(0, cpus)
+        return prev, f"{len(cpus)} of {len(prev)} CPUs (NVML cpu affinity of GPU {local})"
+    except Exception as e:      # no NVML, no permission, ...: run unbound
+        return None, f"unbound ({type(e).__name__}: {e})"
+
+
 def workload_of(args):
     kind, fn, m, l, n, golden, sample = WORKLOADS[args.workload]
     if args.n:
@@ -255,8 +276,12 @@ def run_own_arm(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
+    prev_affinity, binding = None, "not requested"
     if world > 1:   # all ranks stage pageable rows at the same time: share the host's threads instead of oversubscribing them
         os.environ.setdefault("M4RI_B200_STAGE_THREADS", str(max(2, min(12, host_threads() // world))))
+        if os.environ.get("M4RI_B200_BENCH_BIND", "1") != "0":
+            prev_affinity, binding = bind_near_gpu(local)
+        print(f"[bind] rank {rank}: {binding}", file=sys.stderr, flush=True)
     lib = m4ri_b200.load_library()
     if lib.m4ri_b200_device_count() < 1:
         raise SystemExit("no CUDA device: m4ri_b200 has no CPU fallback")
@@ -788,6 +813,8 @@ def run_own_arm(args):
         # which are about to be driven by rank 0
         store = dist.distributed_c10d._get_default_store()
         if rank == 0:
+            if prev_affinity is not None:        # this leg drives every GPU of the box from one process: all CPUs again
+                os.sched_setaffinity(0, prev_affinity)
             fullA = np.empty((m, l // 64), dtype=np.uint64)
             fullB = np.empty((l, n // 64), dtype=np.uint64)
             fullC = np.zeros((m, n // 64), dtype=np.uint64)
@@ -968,6 +995,7 @@ def run_own_arm(args):
                                   ("" if world == 1 else ", NCCL all-gather of B per step" if pc == 1 else
                                    f", NCCL all-gather of B's column block inside each column group ({pr} ranks) per step"),
                    "local_product": [rows, l, ncb],
+                   "cpu_binding": binding,
                    "l2": ("inputs (%d MiB per rank) exceed the 126 MB L2; no flush needed" % (resident_bytes >> 20)) if flush is None
                          else "inputs fit the L2: a 256 MiB buffer is written between timed steps, steps timed one by one"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
